@@ -1,0 +1,158 @@
+/*
+ * petit.h -- C ABI of the B200 (sm_100a) FP4-weight x 16-bit-activation GEMM.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one function of the
+ * reference's C++ API (all citations into /root/reference):
+ *
+ *   petit_gemm_nvfp4_a16        <- fp4::GemmFp4Fp16Grid      lib/gemm/rocm/quantization/gemm.h:120-124
+ *   petit_gemm_mxfp4_a16        <- fp4::GemmMxFp4Fp16Grid    gemm.h:126-130
+ *   petit_get_solutions         <- fp4::GemmGetSolutions     gemm.h:132-133
+ *   petit_repack_fp4_weights    <- fp4::RepackNvFp4ToPetitFp4Weights  gemm.h:135-137
+ *   petit_repack_nvfp4_scales   <- fp4::RepackNvFp4ToPetitFp4Scales   gemm.h:139-141
+ *   petit_repack_mxfp4_scales   <- fp4::RepackMxFp4ToPetitFp4Scales   gemm.h:143-145
+ *   petit_dequant_nvfp4         <- fp4::DequantNvFp4         fp4/quantization_utils.cu:614-645
+ *   petit_dequant_mxfp4         <- fp4::DequantMxFp4         fp4/gemm_fp4.h:19-21
+ *   petit_dequant_packed_nvfp4  <- fp4::DequantPetitFp4      fp4/gemm_fp4.h:11-13
+ *   petit_dequant_packed_mxfp4  <- fp4::DequantPetitMxFp4    fp4/gemm_fp4.h:15-17
+ *   petit_unpack_fp4_weights    (inverse of the repack; round-trip test hook, no reference equivalent)
+ *   petit_hal_*                 <- hal::Device               lib/hal/device.h:8-34
+ *
+ * Differences from the reference, all deliberate:
+ *   - hipStream_t -> cudaStream_t; `unsigned*` payload pointers -> `void*`.
+ *   - the repack functions return an int status (the reference returns void and
+ *     never checks the launch, gemm.h:135-145).
+ *   - the packed layouts are Blackwell tile layouts; they are
+ *     opaque to callers exactly as the reference's are.
+ *
+ * Semantics kept from the reference:
+ *   - return 0 on success, PETIT_ERROR_PROBLEM_SHAPE (1), PETIT_ERROR_KERNEL_SHAPE (2)
+ *     (gemm.h:107-108); petit_get_solutions returns -1 for an unsupported b_type
+ *     (fp4/algo_chooser.cc:20-23); the dequant hooks return -1 on a bad shape or
+ *     type (fp4/quantization_utils.cu:619-621,642).
+ *   - m == 0 || n == 0 || k == 0 is a successful no-op (fp4/gemm_fp4_fp16_grid.cc:42-44).
+ *   - solution_id == (uint64_t)-1 selects the default solution
+ *     (fp4/gemm_fp4_fp16_grid.cc:46-52); other values must come from
+ *     petit_get_solutions.
+ *   - global_scale is a DEVICE pointer, dereferenced inside the kernel
+ *     (fp4/gemm_fp4_fp16_grid.cuh:469-470): no host sync, CUDA-graph safe.
+ *   - everything is asynchronous on the caller's stream; the library owns no
+ *     streams.  MXFP4 requires bf16 activations/outputs
+ *     (fp4/gemm_fp4_fp16_grid.cc:60-63).
+ *
+ * There is no CPU fallback: every function fails (nonzero / CUDA error) when no
+ * sm_100 device is present.
+ */
+#ifndef CAUSALFLOW_PETIT_PETIT_H_
+#define CAUSALFLOW_PETIT_PETIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cudaStream_t without pulling in the CUDA headers. */
+typedef struct CUstream_st *petit_stream_t;
+
+/* Same enumerators, same values as the reference's C++ DataType
+ * (lib/gemm/rocm/quantization/types.h:4-13). */
+typedef enum PetitDataType {
+    PETIT_DTYPE_INT4 = 0,
+    PETIT_DTYPE_FP8_E4M3 = 1,
+    PETIT_DTYPE_FP8_E8M0 = 2,
+    PETIT_DTYPE_FP4_E2M1 = 3,
+    PETIT_DTYPE_FP16 = 4,
+    PETIT_DTYPE_BF16 = 5,
+    PETIT_DTYPE_FP8_E5M2_FNUZ = 6,
+    PETIT_DTYPE_MXFP4_E2M1 = 7
+} PetitDataType;
+
+/* gemm.h:107-108 */
+#define PETIT_OK 0
+#define PETIT_ERROR_PROBLEM_SHAPE 1
+#define PETIT_ERROR_KERNEL_SHAPE 2
+/* Not in the reference: a CUDA runtime/driver failure (launch error, no device). */
+#define PETIT_ERROR_CUDA 3
+
+/* gemm.h:112-117.  require_high_precision is the gfx90a denormal workaround
+ * (lib/pybind/fp4.cc:24-34); it is accepted and ignored on B200, where the one
+ * code path is exact. */
+typedef struct PetitSolutionHints {
+    int32_t a_type; /* PetitDataType: FP16 or BF16 */
+    int32_t b_type; /* PetitDataType: FP4_E2M1 (NVFP4) or MXFP4_E2M1 */
+    int32_t c_type; /* PetitDataType: must equal a_type */
+    int32_t require_high_precision;
+} PetitSolutionHints;
+
+#define PETIT_SOLUTION_AUTO ((uint64_t)-1)
+
+/* C[m,n] (a_type) = A[m,k] (a_type, row-major) x dequant(B)[n,k]^T x *global_scale.
+ * b / scales are the outputs of petit_repack_fp4_weights / petit_repack_nvfp4_scales.
+ * Requires k % 256 == 0 and n % 16 == 0 (lib/pybind/fp4.cc:40-43,82-86). */
+int petit_gemm_nvfp4_a16(void *c, const void *a, const void *b, const void *scales,
+                         const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
+                         const PetitSolutionHints *hints, uint64_t solution_id,
+                         petit_stream_t stream);
+
+/* Same for MXFP4 (group-32 e8m0 scales from petit_repack_mxfp4_scales); bf16 only. */
+int petit_gemm_mxfp4_a16(void *c, const void *a, const void *b, const void *scales,
+                         const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
+                         const PetitSolutionHints *hints, uint64_t solution_id,
+                         petit_stream_t stream);
+
+/* Two-call enumeration (fp4/algo_chooser.cc:14-62): sols may be NULL; *n_sols is the
+ * capacity on entry (ignored when sols is NULL) and the number of applicable
+ * solutions on return.  The values are SolutionId::Repr()-style 64-bit ids. */
+int petit_get_solutions(const PetitSolutionHints *hints, unsigned m, unsigned n, unsigned k,
+                        uint64_t *sols, unsigned *n_sols);
+
+/* in: u32 [out_chan, in_chan/8] row-major, nibble i of a word = element 8w+i;
+ * out: in_chan*out_chan/2 bytes in the packed tile layout. */
+int petit_repack_fp4_weights(uint32_t *out, const uint32_t *in, unsigned in_chan,
+                             unsigned out_chan, petit_stream_t stream);
+int petit_unpack_fp4_weights(uint32_t *out, const uint32_t *in_packed, unsigned in_chan,
+                             unsigned out_chan, petit_stream_t stream);
+
+/* in: e4m3 bytes [out_chan, in_chan/16]; out: same byte count, tile layout, each
+ * byte re-encoded as unsigned E5M3 (exact for every positive finite e4m3). */
+int petit_repack_nvfp4_scales(void *out, const void *in, unsigned in_chan, unsigned out_chan,
+                              petit_stream_t stream);
+/* in: e8m0 bytes [out_chan, in_chan/32]; out: same bytes, tile layout. */
+int petit_repack_mxfp4_scales(void *out, const void *in, unsigned in_chan, unsigned out_chan,
+                              petit_stream_t stream);
+
+/* Dense dequantisation hooks: out is 16-bit [n, k] row-major =
+ * (16-bit)(e2m1 * scale) * (16-bit)global_scale.  out_type is FP16 or BF16 (MXFP4:
+ * BF16 only).  The _packed variants read the repacked layouts. */
+int petit_dequant_nvfp4(void *out, const void *w, const void *scales, float global_scale,
+                        int out_type, unsigned k, unsigned n, petit_stream_t stream);
+int petit_dequant_mxfp4(void *out, const void *w, const void *scales, float global_scale,
+                        int out_type, unsigned k, unsigned n, petit_stream_t stream);
+int petit_dequant_packed_nvfp4(void *out, const void *w_packed, const void *scales_packed,
+                               float global_scale, int out_type, unsigned k, unsigned n,
+                               petit_stream_t stream);
+int petit_dequant_packed_mxfp4(void *out, const void *w_packed, const void *scales_packed,
+                               float global_scale, int out_type, unsigned k, unsigned n,
+                               petit_stream_t stream);
+
+/* Thin device shim (lib/hal/device.h:8-34).  CUDA only; returns 0 or a cudaError_t. */
+int petit_hal_device_count(int *count);
+int petit_hal_set_device(int device);
+int petit_hal_malloc(void **ptr, size_t bytes);
+int petit_hal_free(void *ptr);
+int petit_hal_memset(void *ptr, int value, size_t bytes);
+int petit_hal_copy_to_device(void *dst, const void *src, size_t bytes);
+int petit_hal_copy_to_host(void *dst, const void *src, size_t bytes);
+int petit_hal_synchronize(void);
+
+/* Version of the packed layouts produced by the repack functions. */
+int petit_packed_layout_version(void);
+/* Human-readable name of a solution id ("" if unknown); pointer is static. */
+const char *petit_solution_name(uint64_t solution_id);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* CAUSALFLOW_PETIT_PETIT_H_ */

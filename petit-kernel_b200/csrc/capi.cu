@@ -1,0 +1,336 @@
+// C ABI (include/causalflow/petit/petit.h): argument checking, solution ids,
+// the default-solution chooser, the stream-K workspace and the HAL shim.
+//
+// Replaces the reference's host dispatch layer: GemmFp4Fp16GridImpl / Dispatcher
+// (fp4/gemm_fp4_fp16_grid.cc:11-95), GemmGetSolutions and
+// ChooseDefaultFp4Fp16Solution (fp4/algo_chooser.cc:14-132) and lib/hal
+// (device.h:8-34, rocm/platform_rocm.cc:17-68).  The reference instantiates 234
+// MFMA tile shapes and looks them up in an unordered_map; here a solution is one
+// of five token-tile widths of a single stream-K tcgen05 kernel, encoded in the
+// reference's SolutionId bit layout (gemm.h:33-105) so ids stay opaque 64-bit
+// integers for callers.
+#include "causalflow/petit/petit.h"
+#include "fp4_gemm.h"
+#include "layout.cuh"
+#include "repack.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
+
+namespace {
+
+using namespace petit;
+
+// ---- SolutionId bit layout (gemm.h:33-105) --------------------------------
+constexpr uint64_t kFeatureGrid = 1;
+constexpr uint64_t kElemNv = 1, kElemMx = 2;
+constexpr uint64_t kMfmaF16 = 0, kMfmaBf16 = 1;
+constexpr int kTokVariants[] = {16, 32, 64, 128, 256};
+constexpr int kNumVariants = 5;
+
+constexpr int stage_k_for(int ntok) { return ntok <= 64 ? 256 : (ntok == 128 ? 128 : 64); }
+
+constexpr uint64_t make_solution(int ntok, uint64_t elem_b, uint64_t mfma) {
+    return (uint64_t)(ntok / 16)                              // tile_m  [0,8)
+           | ((uint64_t)(layout::kTileN / 16) << 8)            // tile_n  [8,16)
+           | ((uint64_t)(stage_k_for(ntok) / 64) << 16)        // tile_k  [16,24) in units of 64
+           | (kFeatureGrid << 24)                              // features
+           | (elem_b << 28)                                    // element_b
+           | (mfma << 32)                                      // mfma_type
+           | (1ull << 36) | (4ull << 40) | (2ull << 44);       // warp partition m/n/k, NK
+}
+
+struct Decoded {
+    int ntok;
+    uint64_t elem_b, mfma;
+};
+
+bool decode_solution(uint64_t id, Decoded *d) {
+    d->ntok = (int)(id & 0xff) * 16;
+    d->elem_b = (id >> 28) & 0xf;
+    d->mfma = (id >> 32) & 0xf;
+    bool tok_ok = false;
+    for (int v : kTokVariants) tok_ok |= v == d->ntok;
+    if (!tok_ok) return false;
+    if (d->elem_b != kElemNv && d->elem_b != kElemMx) return false;
+    if (d->mfma != kMfmaF16 && d->mfma != kMfmaBf16) return false;
+    return id == make_solution(d->ntok, d->elem_b, d->mfma);
+}
+
+int default_ntok(unsigned m) {
+    if (const char *e = std::getenv("PETIT_FORCE_NTOK")) {
+        int v = std::atoi(e);
+        for (int t : kTokVariants)
+            if (t == v) return v;
+    }
+    for (int t : kTokVariants)
+        if (m <= (unsigned)t) return t;
+    return 256;
+}
+
+bool problem_shape_ok(unsigned n, unsigned k) {
+    return n % 16 == 0 && k % layout::kTileK == 0;
+}
+
+// ---- per-(device, stream) stream-K workspace --------------------------------
+struct Workspace {
+    float *partials = nullptr;
+    unsigned *counters = nullptr;
+};
+struct DeviceInfo {
+    int num_sms = 0;
+};
+std::mutex g_mu;
+std::map<std::pair<int, cudaStream_t>, Workspace> g_ws;
+std::map<int, DeviceInfo> g_dev;
+
+int get_context(cudaStream_t stream, Workspace *ws, int *num_sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PETIT_ERROR_CUDA;
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto dit = g_dev.find(dev);
+    if (dit == g_dev.end()) {
+        DeviceInfo info;
+        int major = 0;
+        if (cudaDeviceGetAttribute(&info.num_sms, cudaDevAttrMultiProcessorCount, dev) !=
+                cudaSuccess ||
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+            return PETIT_ERROR_CUDA;
+        if (major != 10) return PETIT_ERROR_CUDA; // sm_100a only; no fallback path
+        if (info.num_sms > (int)gemm::kMaxGrid) info.num_sms = gemm::kMaxGrid;
+        dit = g_dev.emplace(dev, info).first;
+    }
+    *num_sms = dit->second.num_sms;
+    auto key = std::make_pair(dev, stream);
+    auto it = g_ws.find(key);
+    if (it == g_ws.end()) {
+        // cudaMalloc is not capturable: step out of a possible stream capture.
+        cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+        cudaThreadExchangeStreamCaptureMode(&mode);
+        Workspace w;
+        cudaError_t e1 = cudaMalloc(&w.partials, gemm::workspace_partials_bytes());
+        cudaError_t e2 = cudaMalloc(&w.counters, gemm::workspace_counters_bytes());
+        cudaError_t e3 =
+            e2 == cudaSuccess ? cudaMemset(w.counters, 0, gemm::workspace_counters_bytes())
+                              : e2;
+        cudaThreadExchangeStreamCaptureMode(&mode);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+            cudaFree(w.partials);
+            cudaFree(w.counters);
+            return PETIT_ERROR_CUDA;
+        }
+        it = g_ws.emplace(key, w).first;
+    }
+    *ws = it->second;
+    return PETIT_OK;
+}
+
+int gemm_impl(void *c, const void *a, const void *b, const void *scales,
+              const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
+              const PetitSolutionHints *hints, uint64_t solution_id, bool force_mx,
+              cudaStream_t stream) {
+    if (m == 0 || n == 0 || k == 0) return PETIT_OK; // gemm_fp4_fp16_grid.cc:42-44
+    if (!hints) return PETIT_ERROR_KERNEL_SHAPE;
+    const bool is_mx = force_mx || hints->b_type == PETIT_DTYPE_MXFP4_E2M1;
+
+    Decoded d;
+    if (solution_id == PETIT_SOLUTION_AUTO) {
+        if (!problem_shape_ok(n, k)) return PETIT_ERROR_PROBLEM_SHAPE;
+        if (hints->a_type != PETIT_DTYPE_FP16 && hints->a_type != PETIT_DTYPE_BF16)
+            return PETIT_ERROR_PROBLEM_SHAPE;
+        d.ntok = default_ntok(m);
+        d.elem_b = is_mx ? kElemMx : kElemNv;
+        d.mfma = hints->a_type == PETIT_DTYPE_BF16 ? kMfmaBf16 : kMfmaF16;
+    } else {
+        if (!decode_solution(solution_id, &d)) return PETIT_ERROR_KERNEL_SHAPE;
+        if (force_mx) d.elem_b = kElemMx; // gemm_fp4_fp16_grid.cc:91-94
+    }
+    if (d.elem_b == kElemMx) {
+        // gemm_fp4_fp16_grid.cc:55-64
+        if (k % 32 != 0) return PETIT_ERROR_PROBLEM_SHAPE;
+        if (hints->a_type != PETIT_DTYPE_BF16 || hints->c_type != PETIT_DTYPE_BF16 ||
+            d.mfma != kMfmaBf16)
+            return PETIT_ERROR_KERNEL_SHAPE;
+    }
+    // an explicit id must agree with the activation type it will be fed
+    if ((d.mfma == kMfmaBf16) != (hints->a_type == PETIT_DTYPE_BF16))
+        return PETIT_ERROR_KERNEL_SHAPE;
+    if (!problem_shape_ok(n, k)) return PETIT_ERROR_PROBLEM_SHAPE; // ConfigSelector::Invoke
+
+    Workspace ws;
+    int num_sms = 0;
+    int err = get_context(stream, &ws, &num_sms);
+    if (err != PETIT_OK) return err;
+
+    gemm::GemmArgs args;
+    args.a = a;
+    args.w = static_cast<const uint8_t *>(b);
+    args.sc = static_cast<const uint8_t *>(scales);
+    args.global_scale = global_scale_dev;
+    args.c = c;
+    args.ws_partials = ws.partials;
+    args.ws_counters = ws.counters;
+    args.m = m;
+    args.n = n;
+    args.k = k;
+    const int mode = d.elem_b == kElemMx
+                         ? gemm::kModeMxBf16
+                         : (d.mfma == kMfmaBf16 ? gemm::kModeNvBf16 : gemm::kModeNvF16);
+    switch (gemm::launch(mode, d.ntok, args, num_sms, stream)) {
+    case gemm::kLaunchOk: return PETIT_OK;
+    case gemm::kLaunchBadShape: return PETIT_ERROR_PROBLEM_SHAPE;
+    case gemm::kLaunchNoKernel: return PETIT_ERROR_KERNEL_SHAPE;
+    default: return PETIT_ERROR_CUDA;
+    }
+}
+
+int dequant_mode(int out_type, bool mx) {
+    if (mx) return out_type == PETIT_DTYPE_BF16 ? gemm::kModeMxBf16 : -1;
+    if (out_type == PETIT_DTYPE_BF16) return gemm::kModeNvBf16;
+    if (out_type == PETIT_DTYPE_FP16) return gemm::kModeNvF16;
+    return -1;
+}
+
+} // namespace
+
+extern "C" {
+
+int petit_gemm_nvfp4_a16(void *c, const void *a, const void *b, const void *scales,
+                         const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
+                         const PetitSolutionHints *hints, uint64_t solution_id,
+                         petit_stream_t stream) {
+    return gemm_impl(c, a, b, scales, global_scale_dev, m, n, k, hints, solution_id, false,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int petit_gemm_mxfp4_a16(void *c, const void *a, const void *b, const void *scales,
+                         const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
+                         const PetitSolutionHints *hints, uint64_t solution_id,
+                         petit_stream_t stream) {
+    return gemm_impl(c, a, b, scales, global_scale_dev, m, n, k, hints, solution_id, true,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int petit_get_solutions(const PetitSolutionHints *hints, unsigned m, unsigned n, unsigned k,
+                        uint64_t *sols, unsigned *n_sols) {
+    (void)m;
+    if (!hints || !n_sols) return -1;
+    // algo_chooser.cc:20-23
+    if (hints->b_type != PETIT_DTYPE_FP4_E2M1 && hints->b_type != PETIT_DTYPE_MXFP4_E2M1)
+        return -1;
+    const bool mx = hints->b_type == PETIT_DTYPE_MXFP4_E2M1;
+    unsigned count = 0;
+    const bool type_ok = (hints->a_type == PETIT_DTYPE_BF16) ||
+                         (hints->a_type == PETIT_DTYPE_FP16 && !mx);
+    if (type_ok && problem_shape_ok(n, k) && n != 0 && k != 0) {
+        const uint64_t mfma = hints->a_type == PETIT_DTYPE_BF16 ? kMfmaBf16 : kMfmaF16;
+        for (int i = 0; i < kNumVariants; ++i) {
+            if (sols && count < *n_sols)
+                sols[count] = make_solution(kTokVariants[i], mx ? kElemMx : kElemNv, mfma);
+            ++count;
+        }
+    }
+    *n_sols = count;
+    return 0;
+}
+
+int petit_repack_fp4_weights(uint32_t *out, const uint32_t *in, unsigned in_chan,
+                             unsigned out_chan, petit_stream_t stream) {
+    return repack::weights(out, in, in_chan, out_chan, false,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int petit_unpack_fp4_weights(uint32_t *out, const uint32_t *in_packed, unsigned in_chan,
+                             unsigned out_chan, petit_stream_t stream) {
+    return repack::weights(out, in_packed, in_chan, out_chan, true,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+int petit_repack_nvfp4_scales(void *out, const void *in, unsigned in_chan, unsigned out_chan,
+                              petit_stream_t stream) {
+    return repack::scales(out, in, in_chan, out_chan, false, false,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+int petit_repack_mxfp4_scales(void *out, const void *in, unsigned in_chan, unsigned out_chan,
+                              petit_stream_t stream) {
+    return repack::scales(out, in, in_chan, out_chan, true, false,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+int petit_dequant_nvfp4(void *out, const void *w, const void *scales, float global_scale,
+                        int out_type, unsigned k, unsigned n, petit_stream_t stream) {
+    const int mode = dequant_mode(out_type, false);
+    if (mode < 0) return -1;
+    return repack::dequant_dense(out, w, scales, global_scale, mode, false, k, n,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
+int petit_dequant_mxfp4(void *out, const void *w, const void *scales, float global_scale,
+                        int out_type, unsigned k, unsigned n, petit_stream_t stream) {
+    const int mode = dequant_mode(out_type, true);
+    if (mode < 0) return -1;
+    return repack::dequant_dense(out, w, scales, global_scale, mode, false, k, n,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
+int petit_dequant_packed_nvfp4(void *out, const void *w_packed, const void *scales_packed,
+                               float global_scale, int out_type, unsigned k, unsigned n,
+                               petit_stream_t stream) {
+    const int mode = dequant_mode(out_type, false);
+    if (mode < 0) return -1;
+    return repack::dequant_dense(out, w_packed, scales_packed, global_scale, mode, true, k, n,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
+int petit_dequant_packed_mxfp4(void *out, const void *w_packed, const void *scales_packed,
+                               float global_scale, int out_type, unsigned k, unsigned n,
+                               petit_stream_t stream) {
+    const int mode = dequant_mode(out_type, true);
+    if (mode < 0) return -1;
+    return repack::dequant_dense(out, w_packed, scales_packed, global_scale, mode, true, k, n,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- HAL shim (lib/hal/device.h:8-34) ---------------------------------------
+int petit_hal_device_count(int *count) { return (int)cudaGetDeviceCount(count); }
+int petit_hal_set_device(int device) { return (int)cudaSetDevice(device); }
+int petit_hal_malloc(void **ptr, size_t bytes) { return (int)cudaMalloc(ptr, bytes); }
+int petit_hal_free(void *ptr) { return (int)cudaFree(ptr); }
+int petit_hal_memset(void *ptr, int value, size_t bytes) {
+    return (int)cudaMemset(ptr, value, bytes);
+}
+int petit_hal_copy_to_device(void *dst, const void *src, size_t bytes) {
+    return (int)cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+}
+int petit_hal_copy_to_host(void *dst, const void *src, size_t bytes) {
+    return (int)cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+}
+int petit_hal_synchronize(void) { return (int)cudaDeviceSynchronize(); }
+
+int petit_packed_layout_version(void) { return layout::kLayoutVersion; }
+
+const char *petit_solution_name(uint64_t solution_id) {
+    static const char *names[3][kNumVariants] = {
+        {"sm100_streamk_nvfp4_f16_tok16", "sm100_streamk_nvfp4_f16_tok32",
+         "sm100_streamk_nvfp4_f16_tok64", "sm100_streamk_nvfp4_f16_tok128",
+         "sm100_streamk_nvfp4_f16_tok256"},
+        {"sm100_streamk_nvfp4_bf16_tok16", "sm100_streamk_nvfp4_bf16_tok32",
+         "sm100_streamk_nvfp4_bf16_tok64", "sm100_streamk_nvfp4_bf16_tok128",
+         "sm100_streamk_nvfp4_bf16_tok256"},
+        {"sm100_streamk_mxfp4_bf16_tok16", "sm100_streamk_mxfp4_bf16_tok32",
+         "sm100_streamk_mxfp4_bf16_tok64", "sm100_streamk_mxfp4_bf16_tok128",
+         "sm100_streamk_mxfp4_bf16_tok256"}};
+    Decoded d;
+    if (!decode_solution(solution_id, &d)) return "";
+    int mode = d.elem_b == kElemMx ? 2 : (d.mfma == kMfmaBf16 ? 1 : 0);
+    if (d.elem_b == kElemMx && d.mfma != kMfmaBf16) return "";
+    for (int i = 0; i < kNumVariants; ++i)
+        if (kTokVariants[i] == d.ntok) return names[mode][i];
+    return "";
+}
+
+} // extern "C"

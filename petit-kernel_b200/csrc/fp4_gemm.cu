@@ -1,0 +1,532 @@
+// FP4-weight x 16-bit-activation GEMM for sm_100a.
+//
+//   C[M,N] = A[M,K] * dequant(W[N,K])^T * global_scale
+//
+// Replaces the reference's GemmFp4Fp16KernelGrid + MultiStagePipeline +
+// WarpPartitionMatmul + BlockReduce + WriteResult
+// (lib/gemm/rocm/quantization/fp4/gemm_fp4_fp16_grid.cuh:199-498,
+//  fp4/warp_schedule_fp16.cuh:10-193, gpu/quantization/reduce.cuh:7-58,
+//  quantization/qgemm.cuh:95-192) with a design built for Blackwell:
+//
+//  * swap-AB: the 128 weight rows of an n-tile are the tcgen05.mma M dimension,
+//    the tokens are the MMA N dimension (16..256), so decode-sized M wastes no
+//    tensor-core rows and each weight is dequantised exactly once per tile.
+//  * TS-form MMA: dequantised weights never touch shared memory.  One dequant
+//    thread owns one weight row = one TMEM lane: it reads 16 bytes (32 fp4) per
+//    ld.shared, converts with cvt.rn.f16x2.e2m1x2 (+ HMUL2 by the block scale),
+//    and writes the 16-bit pairs straight into the A-operand columns of TMEM
+//    with tcgen05.st.  The MMA reads A from TMEM and the token tile (B operand)
+//    from 128B-swizzled shared memory filled by TMA.
+//  * weights + scales arrive through a multi-stage ring of 1-D bulk TMA copies
+//    (cp.async.bulk) of contiguous packed tiles (layout.cuh).
+//  * stream-K: the (n-tile x token-tile x k-tile) unit space is cut into one
+//    contiguous range per SM, so all 148 SMs stream the same number of bytes
+//    whatever the shape.  Tiles cut by a range boundary are reduced through an
+//    fp32 workspace by the last CTA to arrive, in a fixed order (bit-reproducible).
+//  * warp roles: 1 TMA producer, 1 MMA issuer, 8 dequant warps, 4 epilogue
+//    warps; accumulators are double-buffered in TMEM so the epilogue overlaps
+//    the next tile.
+#include "fp4_gemm.h"
+#include "dequant.cuh"
+#include "layout.cuh"
+#include "sm100_ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace petit::gemm {
+
+using namespace petit::ptx;
+using namespace petit::layout;
+using namespace petit::dq;
+
+namespace {
+
+constexpr int kNumDequantWarps = 8;
+constexpr int kNumEpilogueWarps = 4;
+constexpr int kFirstDequantWarp = 2;
+constexpr int kFirstEpilogueWarp = kFirstDequantWarp + kNumDequantWarps;
+constexpr int kNumWarps = kFirstEpilogueWarp + kNumEpilogueWarps;
+constexpr int kNumThreads = kNumWarps * 32;
+constexpr int kEpilogueBarId = 1;
+constexpr int kSmemBudget = 227 * 1024;
+
+template <int MODE, int NTOK, int KS> struct Cfg {
+    static constexpr bool kIsMx = MODE == kModeMxBf16;
+    static constexpr bool kIsBf16 = MODE != kModeNvF16;
+    static constexpr int kSubs = KS / 64;          // 64-k slabs per stage
+    static constexpr int kStagesPerUnit = 256 / KS;
+    static constexpr int kChunks = KS / 32;        // 16-byte chunks per row
+    static constexpr int kScPerSub = kIsMx ? 2 : 4; // scale bytes per row per slab
+    static constexpr int kActBytes = kSubs * NTOK * 128;
+    static constexpr int kWBytes = kChunks * 128 * 16;
+    static constexpr int kScBytes = kSubs * 128 * kScPerSub;
+    static constexpr int kStageBytes =
+        (kActBytes + kWBytes + kScBytes + 1023) / 1024 * 1024;
+    static constexpr int kBarrierBytes = 1024;
+    static constexpr int kStages = (kSmemBudget - kBarrierBytes - 1024) / kStageBytes > 12
+                                       ? 12
+                                       : (kSmemBudget - kBarrierBytes - 1024) / kStageBytes;
+    static constexpr int kNumAcc = NTOK <= 128 ? 2 : 1;
+    static constexpr int kAccCols = kNumAcc * NTOK;
+    static constexpr int kACols = KS / 2;          // TMEM columns of one A stage
+    static constexpr int kAStagesRaw = (512 - kAccCols) / kACols;
+    static constexpr int kAStages = kAStagesRaw > 8 ? 8 : kAStagesRaw;
+    static constexpr int kSmemBytes = kBarrierBytes + kStages * kStageBytes + 1024;
+    static_assert(kStages >= 2, "need at least two smem stages");
+    static_assert(kAStages >= 2, "need at least two TMEM A stages");
+};
+
+struct Barriers {
+    uint64_t full[12];
+    uint64_t empty[12];
+    uint64_t a_full[8];
+    uint64_t a_empty[8];
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
+    uint32_t tmem_base;
+    uint32_t flag;
+};
+static_assert(sizeof(Barriers) <= 1024, "barrier block too large");
+
+// Work decomposition shared by every warp role.
+struct Sched {
+    uint32_t k_tiles, m_tiles, n_tiles;
+    uint64_t total_units;
+    uint32_t grid;
+
+    __device__ __forceinline__ uint64_t begin(uint32_t b) const {
+        return total_units * b / grid;
+    }
+    // CTA that owns unit u (inverse of begin()).
+    __device__ __forceinline__ uint32_t owner(uint64_t u) const {
+        return (uint32_t)(((u + 1) * grid - 1) / total_units);
+    }
+};
+
+struct Segment {
+    uint32_t tile, n_tile, m_tile, kt0, kt1;
+};
+
+__device__ __forceinline__ Segment make_segment(const Sched &s, uint64_t u,
+                                                uint64_t u_end) {
+    Segment g;
+    g.tile = (uint32_t)(u / s.k_tiles);
+    g.kt0 = (uint32_t)(u % s.k_tiles);
+    uint64_t left = u_end - u;
+    uint32_t room = s.k_tiles - g.kt0;
+    g.kt1 = g.kt0 + (uint32_t)(left < room ? left : room);
+    g.n_tile = g.tile / s.m_tiles;
+    g.m_tile = g.tile % s.m_tiles;
+    return g;
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+template <int MODE, int NTOK, int KS>
+__global__ void __launch_bounds__(kNumThreads, 1)
+fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
+    using C = Cfg<MODE, NTOK, KS>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B-swizzled activation slabs
+    uint8_t *smem = reinterpret_cast<uint8_t *>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    Barriers *bars = reinterpret_cast<Barriers *>(smem);
+    uint8_t *stage_base = smem + C::kBarrierBytes;
+
+    const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+    Sched sched;
+    sched.k_tiles = args.k / kTileK;
+    sched.n_tiles = (args.n + kTileN - 1) / kTileN;
+    sched.m_tiles = (args.m + NTOK - 1) / NTOK;
+    sched.total_units = (uint64_t)sched.k_tiles * sched.n_tiles * sched.m_tiles;
+    sched.grid = gridDim.x;
+    const uint64_t u_begin = sched.begin(blockIdx.x);
+    const uint64_t u_end = sched.begin(blockIdx.x + 1);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tmap_act);
+        for (int i = 0; i < C::kStages; ++i) {
+            mbar_init(&bars->full[i], 1);
+            mbar_init(&bars->empty[i], kNumDequantWarps + 1);
+        }
+        for (int i = 0; i < C::kAStages; ++i) {
+            mbar_init(&bars->a_full[i], kNumDequantWarps);
+            mbar_init(&bars->a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->acc_full[i], 1);
+            mbar_init(&bars->acc_empty[i], kNumEpilogueWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem_a0 = tmem + C::kAccCols;
+
+    const uint32_t k_bytes_half = args.k / 2;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint64_t pol_stream = policy_evict_first();
+            uint32_t it = 0;
+            for (uint64_t u = u_begin; u < u_end;) {
+                const Segment g = make_segment(sched, u, u_end);
+                const uint32_t rows = tile_rows(args.n, g.n_tile);
+                const uint8_t *w_tile =
+                    args.w + (size_t)g.n_tile * kTileN * k_bytes_half;
+                const uint8_t *sc_tile =
+                    args.sc + (size_t)g.n_tile * kTileN * (args.k / 64) * C::kScPerSub;
+                const uint32_t w_stage_bytes = C::kChunks * rows * 16;
+                const uint32_t sc_stage_bytes = C::kSubs * rows * C::kScPerSub;
+                for (uint32_t kt = g.kt0; kt < g.kt1; ++kt) {
+#pragma unroll 1
+                    for (int sub = 0; sub < C::kStagesPerUnit; ++sub, ++it) {
+                        const uint32_t s = it % C::kStages;
+                        const uint32_t ph = (it / C::kStages) & 1;
+                        mbar_wait(&bars->empty[s], ph ^ 1);
+                        uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
+                        mbar_arrive_expect_tx(&bars->full[s],
+                                              C::kActBytes + w_stage_bytes + sc_stage_bytes);
+                        // weights: contiguous chunk range of the packed unit
+                        bulk_g2s_hint(st + C::kActBytes,
+                                      w_tile + (size_t)kt * rows * 128 +
+                                          (size_t)sub * w_stage_bytes,
+                                      w_stage_bytes, &bars->full[s], pol_stream);
+                        bulk_g2s_hint(st + C::kActBytes + C::kWBytes,
+                                      sc_tile + (size_t)kt * rows * 4 * C::kScPerSub +
+                                          (size_t)sub * sc_stage_bytes,
+                                      sc_stage_bytes, &bars->full[s], pol_stream);
+                        // token tile: box {64 k, NTOK tokens, kSubs slabs}
+                        tma_load_3d(st, &tmap_act, &bars->full[s], 0, g.m_tile * NTOK,
+                                    kt * 4 + sub * C::kSubs);
+                    }
+                }
+                u += g.kt1 - g.kt0;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(
+                C::kIsBf16 ? kFmtBF16 : kFmtF16, C::kIsBf16 ? kFmtBF16 : kFmtF16, 128, NTOK);
+            uint32_t it = 0, seg = 0;
+            for (uint64_t u = u_begin; u < u_end; ++seg) {
+                const Segment g = make_segment(sched, u, u_end);
+                const uint32_t acc = seg % C::kNumAcc;
+                const uint32_t acc_ph = (seg / C::kNumAcc) & 1;
+                mbar_wait(&bars->acc_empty[acc], acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + acc * NTOK;
+                const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
+                for (uint32_t i = 0; i < n_stage; ++i, ++it) {
+                    const uint32_t s = it % C::kStages;
+                    const uint32_t ph = (it / C::kStages) & 1;
+                    const uint32_t ta = it % C::kAStages;
+                    const uint32_t ta_ph = (it / C::kAStages) & 1;
+                    mbar_wait(&bars->full[s], ph);      // token tile landed
+                    mbar_wait(&bars->a_full[ta], ta_ph); // weights are in TMEM
+                    tc_fence_after();
+                    const uint32_t act_addr =
+                        smem_u32(stage_base + (size_t)s * C::kStageBytes);
+                    const uint32_t a_tmem = tmem_a0 + ta * C::kACols;
+#pragma unroll
+                    for (int j = 0; j < KS / 16; ++j) {
+                        const uint64_t bdesc = make_smem_desc_sw128(
+                            act_addr + (j / 4) * (NTOK * 128) + (j % 4) * 32);
+                        mma_f16_ts(d_tmem, a_tmem + j * 8, bdesc, idesc,
+                                   (i | (uint32_t)j) != 0);
+                    }
+                    tc_commit(&bars->a_empty[ta]);
+                    tc_commit(&bars->empty[s]);
+                }
+                tc_commit(&bars->acc_full[acc]);
+                u += g.kt1 - g.kt0;
+            }
+        }
+    } else if (warp < kFirstEpilogueWarp) {
+        // ===================== dequant warps =====================
+        const uint32_t dw = warp - kFirstDequantWarp;
+        const uint32_t quarter = warp % 4;     // TMEM lane quarter this warp may touch
+        const uint32_t khalf = dw / 4;         // which half of the stage's k range
+        const uint32_t row = quarter * 32 + lane;
+        const uint32_t lane_base = (quarter * 32) << 16;
+        constexpr int kMyChunks = C::kChunks / 2 > 0 ? C::kChunks / 2 : 1;
+        uint32_t it = 0;
+        for (uint64_t u = u_begin; u < u_end;) {
+            const Segment g = make_segment(sched, u, u_end);
+            const uint32_t rows = tile_rows(args.n, g.n_tile);
+            const bool active = row < rows;
+            const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
+            for (uint32_t i = 0; i < n_stage; ++i, ++it) {
+                const uint32_t s = it % C::kStages;
+                const uint32_t ph = (it / C::kStages) & 1;
+                const uint32_t ta = it % C::kAStages;
+                const uint32_t ta_ph = (it / C::kAStages) & 1;
+                const uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
+                const uint8_t *wsm = st + C::kActBytes;
+                const uint8_t *scsm = wsm + C::kWBytes;
+                mbar_wait(&bars->full[s], ph);
+                // stage inputs -> registers
+                uint4 q[kMyChunks];
+                uint32_t scw[kMyChunks];
+#pragma unroll
+                for (int ci = 0; ci < kMyChunks; ++ci) {
+                    const int c = (C::kChunks >= 2) ? (int)khalf * kMyChunks + ci : 0;
+                    if (active) {
+                        q[ci] = *reinterpret_cast<const uint4 *>(
+                            wsm + (size_t)c * rows * 16 + row * 16);
+                        const int ksub = c / 2;
+                        if (C::kIsMx) {
+                            uint32_t hw = *reinterpret_cast<const uint16_t *>(
+                                scsm + (size_t)ksub * rows * 2 + row * 2);
+                            scw[ci] = (hw >> ((c & 1) * 8)) & 0xff;
+                        } else {
+                            uint32_t w32 = *reinterpret_cast<const uint32_t *>(
+                                scsm + (size_t)ksub * rows * 4 + row * 4);
+                            scw[ci] = (w32 >> ((c & 1) * 16)) & 0xffff;
+                        }
+                    } else {
+                        q[ci] = make_uint4(0, 0, 0, 0);
+                        scw[ci] = 0;
+                    }
+                }
+                // the previous occupant of this TMEM A stage must have been consumed
+                mbar_wait(&bars->a_empty[ta], ta_ph ^ 1);
+                tc_fence_after();
+                if (C::kChunks >= 2 || khalf == 0) {
+#pragma unroll
+                    for (int ci = 0; ci < kMyChunks; ++ci) {
+                        const int c = (C::kChunks >= 2) ? (int)khalf * kMyChunks + ci : 0;
+                        bool two0 = false, two1 = false;
+                        uint32_t m0, m1;
+                        if (C::kIsMx) {
+                            m0 = scale_multiplier<MODE>(scw[ci], two0);
+                            m1 = m0;
+                        } else {
+                            m0 = scale_multiplier<MODE>(scw[ci] & 0xff, two0);
+                            m1 = scale_multiplier<MODE>(scw[ci] >> 8, two1);
+                        }
+                        uint32_t out[16];
+                        dequant_chunk<MODE>(q[ci], m0, m1, two0, out);
+                        tmem_st_x16(tmem_a0 + lane_base + ta * C::kACols + c * 16, out);
+                    }
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&bars->a_full[ta]);
+                    mbar_arrive(&bars->empty[s]);
+                }
+            }
+            u += g.kt1 - g.kt0;
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const uint32_t quarter = warp % 4;
+        const uint32_t ew_tid = threadIdx.x - kFirstEpilogueWarp * 32; // 0..127
+        const uint32_t row = quarter * 32 + lane;
+        const uint32_t lane_base = (quarter * 32) << 16;
+        float gs = *args.global_scale;
+        gs *= epilogue_factor<MODE>(); // power of two folded out of the MX multiplier
+        uint32_t seg = 0;
+        for (uint64_t u = u_begin; u < u_end; ++seg) {
+            const Segment g = make_segment(sched, u, u_end);
+            const uint32_t rows = tile_rows(args.n, g.n_tile);
+            const uint32_t acc = seg % C::kNumAcc;
+            const uint32_t acc_ph = (seg / C::kNumAcc) & 1;
+            const bool full_k = g.kt0 == 0 && g.kt1 == sched.k_tiles;
+            const uint32_t n_idx = g.n_tile * kTileN + row;
+            const uint32_t m0 = g.m_tile * NTOK;
+            const uint32_t m_valid = args.m - m0 < (uint32_t)NTOK ? args.m - m0 : NTOK;
+            const bool row_ok = row < rows;
+
+            // partial-tile bookkeeping
+            const uint64_t tile_u0 = (uint64_t)g.tile * sched.k_tiles;
+            const uint32_t b_first = sched.owner(tile_u0);
+            const uint32_t b_last = sched.owner(tile_u0 + sched.k_tiles - 1);
+            const uint32_t my_slot =
+                blockIdx.x * 2 + ((u == u_begin) ? 0u : 1u);
+            float *slot = args.ws_partials + (size_t)my_slot * (kTileN * NTOK);
+
+            mbar_wait(&bars->acc_full[acc], acc_ph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < NTOK; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld_x16(tmem + lane_base + acc * NTOK + c0, v);
+                tmem_wait_ld();
+                if (full_k) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t t = c0 + j;
+                            if (t < m_valid) {
+                                const float r = __uint_as_float(v[j]) * gs;
+                                const size_t off = (size_t)(m0 + t) * args.n + n_idx;
+                                if (C::kIsBf16)
+                                    reinterpret_cast<__nv_bfloat16 *>(args.c)[off] =
+                                        __float2bfloat16_rn(r);
+                                else
+                                    reinterpret_cast<__half *>(args.c)[off] =
+                                        __float2half_rn(r);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        __stcg(&slot[(size_t)(c0 + j) * kTileN + row],
+                               __uint_as_float(v[j]));
+                }
+            }
+            // accumulator drained -> MMA may reuse it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+
+            if (!full_k) {
+                __threadfence();
+                named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
+                if (ew_tid == 0) {
+                    const uint32_t old = atomicAdd(&args.ws_counters[g.tile], 1u);
+                    bars->flag = old;
+                }
+                named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
+                const uint32_t old = bars->flag;
+                const uint32_t nseg = b_last - b_first + 1;
+                if (old == nseg - 1) {
+                    // last to arrive: reduce all partials in CTA order
+                    __threadfence();
+                    if (row_ok) {
+#pragma unroll 1
+                        for (uint32_t t = 0; t < m_valid; ++t) {
+                            float sum = 0.f;
+                            for (uint32_t b = b_first; b <= b_last; ++b) {
+                                const uint64_t bu0 = sched.begin(b);
+                                const uint32_t sl =
+                                    b * 2 + ((bu0 / sched.k_tiles) == g.tile ? 0u : 1u);
+                                sum += __ldcg(args.ws_partials +
+                                              (size_t)sl * (kTileN * NTOK) +
+                                              (size_t)t * kTileN + row);
+                            }
+                            const float r = sum * gs;
+                            const size_t off = (size_t)(m0 + t) * args.n + n_idx;
+                            if (C::kIsBf16)
+                                reinterpret_cast<__nv_bfloat16 *>(args.c)[off] =
+                                    __float2bfloat16_rn(r);
+                            else
+                                reinterpret_cast<__half *>(args.c)[off] = __float2half_rn(r);
+                        }
+                    }
+                    if (ew_tid == 0) args.ws_counters[g.tile] = 0; // self-cleaning
+                }
+                // flag is reused by the next partial segment
+                named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
+            }
+            u += g.kt1 - g.kt0;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+                cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+template <int MODE, int NTOK, int KS>
+int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
+    using C = Cfg<MODE, NTOK, KS>;
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) return kLaunchCudaError;
+
+    // activations [M, K] 16-bit row-major viewed as (64, M, K/64)
+    CUtensorMap tmap;
+    const cuuint64_t dims[3] = {64, args.m, args.k / 64};
+    const cuuint64_t strides[2] = {(cuuint64_t)args.k * 2, 128};
+    const cuuint32_t box[3] = {64, (cuuint32_t)NTOK, (cuuint32_t)C::kSubs};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tmap,
+                        C::kIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                   : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                        3, const_cast<void *>(args.a), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return kLaunchCudaError;
+
+    static bool attr_set[64] = {}; // per instantiation, per device
+    auto kern = fp4_gemm_kernel<MODE, NTOK, KS>;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return kLaunchCudaError;
+    if (!attr_set[dev & 63]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::kSmemBytes) != cudaSuccess)
+            return kLaunchCudaError;
+        attr_set[dev & 63] = true;
+    }
+    const uint64_t n_tiles = (args.n + kTileN - 1) / kTileN;
+    const uint64_t m_tiles = (args.m + NTOK - 1) / NTOK;
+    const uint64_t units = n_tiles * m_tiles * (args.k / kTileK);
+    const unsigned grid = (unsigned)(units < (uint64_t)num_sms ? units : (uint64_t)num_sms);
+    if (m_tiles * n_tiles > kMaxTiles || grid > kMaxGrid) return kLaunchBadShape;
+    kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmap, args);
+    return cudaGetLastError() == cudaSuccess ? kLaunchOk : kLaunchCudaError;
+}
+
+template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
+                                    cudaStream_t stream) {
+    switch (ntok) {
+    case 16: return launch_variant<MODE, 16, 256>(args, num_sms, stream);
+    case 32: return launch_variant<MODE, 32, 256>(args, num_sms, stream);
+    case 64: return launch_variant<MODE, 64, 256>(args, num_sms, stream);
+    case 128: return launch_variant<MODE, 128, 128>(args, num_sms, stream);
+    case 256: return launch_variant<MODE, 256, 64>(args, num_sms, stream);
+    default: return kLaunchNoKernel;
+    }
+}
+
+} // namespace
+
+size_t workspace_partials_bytes() {
+    return (size_t)kMaxGrid * 2 * kTileN * 256 * sizeof(float);
+}
+size_t workspace_counters_bytes() { return (size_t)kMaxTiles * sizeof(unsigned); }
+
+int launch(int mode, int ntok, const GemmArgs &args, int num_sms, cudaStream_t stream) {
+    switch (mode) {
+    case kModeNvF16: return launch_mode<kModeNvF16>(args, ntok, num_sms, stream);
+    case kModeNvBf16: return launch_mode<kModeNvBf16>(args, ntok, num_sms, stream);
+    case kModeMxBf16: return launch_mode<kModeMxBf16>(args, ntok, num_sms, stream);
+    default: return kLaunchNoKernel;
+    }
+}
+
+} // namespace petit::gemm

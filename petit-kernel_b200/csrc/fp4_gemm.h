@@ -1,0 +1,33 @@
+// Internal interface between the C ABI (capi.cu) and the GEMM kernels.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace petit::gemm {
+
+enum : int { kModeNvF16 = 0, kModeNvBf16 = 1, kModeMxBf16 = 2 };
+enum : int { kLaunchOk = 0, kLaunchBadShape = 1, kLaunchNoKernel = 2, kLaunchCudaError = 3 };
+
+constexpr unsigned kMaxGrid = 160;         // >= SM count of any sm_100 part
+constexpr unsigned kMaxTiles = 1u << 20;   // (n-tiles x token-tiles) upper bound
+
+struct GemmArgs {
+    const void *a;          // [m, k] 16-bit row-major
+    const uint8_t *w;       // packed fp4 (layout.cuh)
+    const uint8_t *sc;      // packed scales
+    const float *global_scale; // device pointer
+    void *c;                // [m, n] 16-bit row-major
+    float *ws_partials;     // stream-K partial tiles
+    unsigned *ws_counters;  // per-tile arrival counters (zero between launches)
+    uint32_t m, n, k;
+};
+
+size_t workspace_partials_bytes();
+size_t workspace_counters_bytes();
+
+// ntok: tokens per MMA (16, 32, 64, 128, 256).
+int launch(int mode, int ntok, const GemmArgs &args, int num_sms, cudaStream_t stream);
+
+} // namespace petit::gemm

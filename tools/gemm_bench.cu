@@ -1,0 +1,103 @@
+// Kernel-only timing of the C ABI GEMM on synthetic packed data (no parity
+// check -- tests/ does that).  Rotates over enough distinct weight copies to
+// defeat the 126 MB L2.  Usage: gemm_bench [nv|mx] [bf16|f16] [reps]
+#include "causalflow/petit/petit.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
+#include <vector>
+
+#define CK(x)                                                                             \
+    do {                                                                                  \
+        cudaError_t e_ = (x);                                                             \
+        if (e_ != cudaSuccess) {                                                          \
+            printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            exit(1);                                                                      \
+        }                                                                                 \
+    } while (0)
+
+__global__ void fill_kernel(uint32_t *p, size_t n, uint32_t seed, uint32_t mask, uint32_t orv) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t x = (uint32_t)i * 2654435761u + seed;
+        x ^= x >> 15; x *= 0x2c1b3c6du; x ^= x >> 12; x *= 0x297a2d39u; x ^= x >> 15;
+        p[i] = (x & mask) | orv;
+    }
+}
+
+int main(int argc, char **argv) {
+    bool mx = argc > 1 && !strcmp(argv[1], "mx");
+    bool bf16 = !(argc > 2 && !strcmp(argv[2], "f16"));
+    int reps = argc > 3 ? atoi(argv[3]) : 40;
+    const char *only = argc > 4 ? argv[4] : "";
+    struct Shape { const char *name; unsigned n, k; };
+    const Shape shapes[] = {{"qkv", 10240, 8192}, {"o", 8192, 8192}, {"gate_up", 57344, 8192},
+                            {"down", 8192, 28672}};
+    std::vector<unsigned> ms = {1, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192};
+    if (argc > 5) { ms.clear(); ms.push_back(atoi(argv[5])); }
+    const double hbm_peak = 6535.7, tf_peak = 1600.2;
+    float *d_gs;
+    float one = 1.0f;
+    CK(cudaMalloc(&d_gs, 4));
+    CK(cudaMemcpy(d_gs, &one, 4, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (const Shape &s : shapes) {
+        if (only[0] && strcmp(only, s.name) && strcmp(only, "all")) continue;
+        const size_t wbytes = (size_t)s.n * s.k / 2, sbytes = (size_t)s.n * s.k / (mx ? 32 : 16);
+        int copies = (int)std::max<size_t>(2, (size_t)400e6 / (wbytes + sbytes) + 1);
+        uint8_t *w, *sc;
+        CK(cudaMalloc(&w, wbytes * copies));
+        CK(cudaMalloc(&sc, sbytes * copies));
+        fill_kernel<<<1184, 256>>>((uint32_t *)w, wbytes * copies / 4, 1, 0xffffffffu, 0);
+        // scales: NV E5M3 bytes with e5 in [8,23] ; MX e8m0 in [112,143]
+        if (mx) fill_kernel<<<1184, 256>>>((uint32_t *)sc, sbytes * copies / 4, 2, 0x1f1f1f1fu, 0x70707070u);
+        else fill_kernel<<<1184, 256>>>((uint32_t *)sc, sbytes * copies / 4, 2, 0x3f3f3f3fu, 0x40404040u);
+        for (unsigned m : ms) {
+            uint16_t *a, *c;
+            CK(cudaMalloc(&a, (size_t)m * s.k * 2));
+            CK(cudaMalloc(&c, (size_t)m * s.n * 2));
+            // activations: small bf16/f16 values (exponent field mid-range)
+            fill_kernel<<<1184, 256>>>((uint32_t *)a, (size_t)m * s.k / 2, 3,
+                                       bf16 ? 0x807f807fu : 0x83ff83ffu, bf16 ? 0x3f003f00u : 0x38003800u);
+            CK(cudaDeviceSynchronize());
+            int t = bf16 ? PETIT_DTYPE_BF16 : PETIT_DTYPE_FP16;
+            PetitSolutionHints hints = {t, mx ? PETIT_DTYPE_MXFP4_E2M1 : PETIT_DTYPE_FP4_E2M1, t, 0};
+            auto call = [&](int i) {
+                const uint8_t *wp = w + (size_t)(i % copies) * wbytes;
+                const uint8_t *sp = sc + (size_t)(i % copies) * sbytes;
+                int rc = mx ? petit_gemm_mxfp4_a16(c, a, wp, sp, d_gs, m, s.n, s.k, &hints,
+                                                   PETIT_SOLUTION_AUTO, nullptr)
+                            : petit_gemm_nvfp4_a16(c, a, wp, sp, d_gs, m, s.n, s.k, &hints,
+                                                   PETIT_SOLUTION_AUTO, nullptr);
+                if (rc) { printf("gemm rc=%d\n", rc); exit(1); }
+            };
+            int r = m >= 1024 ? std::max(4, reps / 8) : reps;
+            for (int i = 0; i < 5; ++i) call(i);
+            CK(cudaDeviceSynchronize());
+            // back-to-back launches (includes launch gaps), then per-launch events
+            CK(cudaEventRecord(e0));
+            for (int i = 0; i < r; ++i) call(i);
+            CK(cudaEventRecord(e1));
+            CK(cudaDeviceSynchronize());
+            float ms_total;
+            cudaEventElapsedTime(&ms_total, e0, e1);
+            double us = ms_total * 1e3 / r;
+            double bytes = (double)wbytes + sbytes + 2.0 * m * s.k + 2.0 * m * s.n + 4;
+            double flops = 2.0 * m * s.n * s.k;
+            printf("%-7s %s %s M=%-5u  %9.2f us  %7.0f GB/s (%5.1f%% of %.0f)  %7.1f TFLOPS (%5.1f%% of %.0f)\n",
+                   s.name, mx ? "mx" : "nv", bf16 ? "bf16" : "f16 ", m, us, bytes / us * 1e-3,
+                   bytes / us * 1e-3 / hbm_peak * 100, hbm_peak, flops / us * 1e-6,
+                   flops / us * 1e-6 / tf_peak * 100, tf_peak);
+            cudaFree(a);
+            cudaFree(c);
+        }
+        cudaFree(w);
+        cudaFree(sc);
+    }
+    return 0;
+}

@@ -176,6 +176,7 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
     args.m = m;
     args.n = n;
     args.k = k;
+    args.two29 = 1u << 29;
     const int mode = d.elem_b == kElemMx
                          ? gemm::kModeMxBf16
                          : (d.mfma == kMfmaBf16 ? gemm::kModeNvBf16 : gemm::kModeNvF16);

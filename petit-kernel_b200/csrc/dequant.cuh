@@ -42,15 +42,18 @@ __device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
 // of (value * 2^-112): shift the exponent/mantissa down by 3 and move the sign
 // from bit 12 back to bit 15 (adding 0x7000 carries it up; the mask drops the
 // carry trail).
-__device__ __forceinline__ uint32_t f16x2_to_bf16x2_scaled(uint32_t h) {
-    uint32_t t = __umulhi(h, 1u << 29) + 0x70007000u;
+// The shift runs on the FMA pipe as IMAD.HI (mad.hi with a 2^29 multiplier that
+// arrives as a kernel argument, so ptxas cannot strength-reduce it to LEA.HI/SHF) because the ALU pipe (F2FP, LOP3, SHF, LEA: 64 lanes/clk/SM) is
+// the measured bottleneck of the decode path.
+__device__ __forceinline__ uint32_t f16x2_to_bf16x2_scaled(uint32_t h, uint32_t two29) {
+    uint32_t t;
+    asm("mad.hi.u32 %0, %1, %2, 0x70007000;" : "=r"(t) : "r"(h), "r"(two29));
     return t & 0x8fff8fffu;
 }
-
 template <int MODE>
 __device__ __forceinline__ void dequant_chunk(const uint4 q, uint32_t mult0,
                                               uint32_t mult1, bool two_step,
-                                              uint32_t (&out)[16]) {
+                                              uint32_t two29, uint32_t (&out)[16]) {
     const uint32_t words[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
@@ -64,9 +67,9 @@ __device__ __forceinline__ void dequant_chunk(const uint4 q, uint32_t mult0,
             if (MODE == kModeNvF16) {
                 out[w * 4 + j] = hmul2_f16(h[j], mult);
             } else if (MODE == kModeNvBf16) {
-                out[w * 4 + j] = hmul2_bf16(f16x2_to_bf16x2_scaled(h[j]), mult);
+                out[w * 4 + j] = hmul2_bf16(f16x2_to_bf16x2_scaled(h[j], two29), mult);
             } else {
-                uint32_t t = f16x2_to_bf16x2_scaled(h[j]);
+                uint32_t t = f16x2_to_bf16x2_scaled(h[j], two29);
                 if (two_step) t = hmul2_bf16(t, 0x77807780u); // * 2^112
                 out[w * 4 + j] = hmul2_bf16(t, mult);
             }

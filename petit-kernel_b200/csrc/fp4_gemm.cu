@@ -65,11 +65,17 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     static constexpr int kStageBytes =
         (kActBytes + kWBytes + kScBytes + 1023) / 1024 * 1024;
     static constexpr int kBarrierBytes = 1024;
-    static constexpr int kStages = (kSmemBudget - kBarrierBytes - 1024) / kStageBytes > 12
-                                       ? 12
+    static constexpr int kStages = (kSmemBudget - kBarrierBytes - 1024) / kStageBytes > 16
+                                       ? 16
                                        : (kSmemBudget - kBarrierBytes - 1024) / kStageBytes;
+    // Small-N MMAs that accumulate into the same TMEM columns serialise on the
+    // full MMA latency (~130 clk measured), so consecutive k-steps rotate over
+    // kChains independent accumulators that the epilogue sums.
+    static constexpr int kChains = NTOK >= 128 ? 1 : 128 / NTOK;
     static constexpr int kNumAcc = NTOK <= 128 ? 2 : 1;
-    static constexpr int kAccCols = kNumAcc * NTOK;
+    static constexpr int kAccBufCols = kChains * NTOK;
+    static constexpr int kAccCols = kNumAcc * kAccBufCols;
+    static_assert(KS / 16 >= kChains, "stage must cover every accumulator chain");
     static constexpr int kACols = KS / 2;          // TMEM columns of one A stage
     static constexpr int kAStagesRaw = (512 - kAccCols) / kACols;
     static constexpr int kAStages = kAStagesRaw > 8 ? 8 : kAStagesRaw;
@@ -79,8 +85,8 @@ template <int MODE, int NTOK, int KS> struct Cfg {
 };
 
 struct Barriers {
-    uint64_t full[12];
-    uint64_t empty[12];
+    uint64_t full[16];
+    uint64_t empty[16];
     uint64_t a_full[8];
     uint64_t a_empty[8];
     uint64_t acc_full[2];
@@ -120,6 +126,31 @@ __device__ __forceinline__ Segment make_segment(const Sched &s, uint64_t u,
     g.n_tile = g.tile / s.m_tiles;
     g.m_tile = g.tile % s.m_tiles;
     return g;
+}
+
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+template <bool kBf16>
+__device__ __forceinline__ void store_out(void *c, size_t off, float r) {
+    if (kBf16)
+        reinterpret_cast<__nv_bfloat16 *>(c)[off] = __float2bfloat16_rn(r);
+    else
+        reinterpret_cast<__half *>(c)[off] = __float2half_rn(r);
 }
 
 // ---------------------------------------------------------------------------
@@ -174,82 +205,85 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            const uint64_t pol_stream = policy_evict_first();
-            uint32_t it = 0;
-            for (uint64_t u = u_begin; u < u_end;) {
-                const Segment g = make_segment(sched, u, u_end);
-                const uint32_t rows = tile_rows(args.n, g.n_tile);
-                const uint8_t *w_tile =
-                    args.w + (size_t)g.n_tile * kTileN * k_bytes_half;
-                const uint8_t *sc_tile =
-                    args.sc + (size_t)g.n_tile * kTileN * (args.k / 64) * C::kScPerSub;
-                const uint32_t w_stage_bytes = C::kChunks * rows * 16;
-                const uint32_t sc_stage_bytes = C::kSubs * rows * C::kScPerSub;
-                for (uint32_t kt = g.kt0; kt < g.kt1; ++kt) {
-#pragma unroll 1
-                    for (int sub = 0; sub < C::kStagesPerUnit; ++sub, ++it) {
-                        const uint32_t s = it % C::kStages;
-                        const uint32_t ph = (it / C::kStages) & 1;
-                        mbar_wait(&bars->empty[s], ph ^ 1);
-                        uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
-                        mbar_arrive_expect_tx(&bars->full[s],
-                                              C::kActBytes + w_stage_bytes + sc_stage_bytes);
-                        // weights: contiguous chunk range of the packed unit
-                        bulk_g2s_hint(st + C::kActBytes,
-                                      w_tile + (size_t)kt * rows * 128 +
-                                          (size_t)sub * w_stage_bytes,
-                                      w_stage_bytes, &bars->full[s], pol_stream);
-                        bulk_g2s_hint(st + C::kActBytes + C::kWBytes,
-                                      sc_tile + (size_t)kt * rows * 4 * C::kScPerSub +
-                                          (size_t)sub * sc_stage_bytes,
-                                      sc_stage_bytes, &bars->full[s], pol_stream);
-                        // token tile: box {64 k, NTOK tokens, kSubs slabs}
-                        tma_load_3d(st, &tmap_act, &bars->full[s], 0, g.m_tile * NTOK,
-                                    kt * 4 + sub * C::kSubs);
-                    }
+        // The loop is executed by the whole (converged) warp so that every value is
+        // warp-uniform; only the async instructions are issued by one elected lane.
+        const uint64_t pol_stream = policy_evict_first();
+        uint32_t it = 0;
+        for (uint64_t u = u_begin; u < u_end;) {
+            const Segment g = make_segment(sched, u, u_end);
+            const uint32_t rows = tile_rows(args.n, g.n_tile);
+            const uint8_t *w_tile = args.w + (size_t)g.n_tile * kTileN * k_bytes_half;
+            const uint8_t *sc_tile =
+                args.sc + (size_t)g.n_tile * kTileN * (args.k / 64) * C::kScPerSub;
+            const uint32_t w_stage_bytes = C::kChunks * rows * 16;
+            const uint32_t sc_stage_bytes = C::kSubs * rows * C::kScPerSub;
+            const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
+            const uint8_t *w_src = w_tile + (size_t)g.kt0 * rows * 128;
+            const uint8_t *sc_src = sc_tile + (size_t)g.kt0 * rows * 4 * C::kScPerSub;
+            int32_t k_slab = (int32_t)(g.kt0 * 4);
+            for (uint32_t i = 0; i < n_stage; ++i, ++it) {
+                const uint32_t s = it % C::kStages;
+                const uint32_t ph = (it / C::kStages) & 1;
+                mbar_wait(&bars->empty[s], ph ^ 1);
+                if (elect_one()) {
+                    uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
+                    mbar_arrive_expect_tx(&bars->full[s],
+                                          C::kActBytes + w_stage_bytes + sc_stage_bytes);
+                    bulk_g2s_hint(st + C::kActBytes, w_src, w_stage_bytes, &bars->full[s],
+                                  pol_stream);
+                    bulk_g2s_hint(st + C::kActBytes + C::kWBytes, sc_src, sc_stage_bytes,
+                                  &bars->full[s], pol_stream);
+                    // token tile: box {64 k, NTOK tokens, kSubs slabs}
+                    tma_load_3d(st, &tmap_act, &bars->full[s], 0, g.m_tile * NTOK, k_slab);
                 }
-                u += g.kt1 - g.kt0;
+                __syncwarp();
+                w_src += w_stage_bytes;
+                sc_src += sc_stage_bytes;
+                k_slab += C::kSubs;
             }
+            u += g.kt1 - g.kt0;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(
-                C::kIsBf16 ? kFmtBF16 : kFmtF16, C::kIsBf16 ? kFmtBF16 : kFmtF16, 128, NTOK);
-            uint32_t it = 0, seg = 0;
-            for (uint64_t u = u_begin; u < u_end; ++seg) {
-                const Segment g = make_segment(sched, u, u_end);
-                const uint32_t acc = seg % C::kNumAcc;
-                const uint32_t acc_ph = (seg / C::kNumAcc) & 1;
-                mbar_wait(&bars->acc_empty[acc], acc_ph ^ 1);
+        constexpr uint32_t idesc = make_idesc_f16(
+            C::kIsBf16 ? kFmtBF16 : kFmtF16, C::kIsBf16 ? kFmtBF16 : kFmtF16, 128, NTOK);
+        const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(stage_base));
+        uint32_t it = 0, seg = 0;
+        for (uint64_t u = u_begin; u < u_end; ++seg) {
+            const Segment g = make_segment(sched, u, u_end);
+            const uint32_t acc = seg % C::kNumAcc;
+            const uint32_t acc_ph = (seg / C::kNumAcc) & 1;
+            mbar_wait(&bars->acc_empty[acc], acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + acc * C::kAccBufCols;
+            const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
+            for (uint32_t i = 0; i < n_stage; ++i, ++it) {
+                const uint32_t s = it % C::kStages;
+                const uint32_t ph = (it / C::kStages) & 1;
+                const uint32_t ta = it % C::kAStages;
+                const uint32_t ta_ph = (it / C::kAStages) & 1;
+                mbar_wait(&bars->full[s], ph);      // token tile landed
+                mbar_wait(&bars->a_full[ta], ta_ph); // weights are in TMEM
                 tc_fence_after();
-                const uint32_t d_tmem = tmem + acc * NTOK;
-                const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
-                for (uint32_t i = 0; i < n_stage; ++i, ++it) {
-                    const uint32_t s = it % C::kStages;
-                    const uint32_t ph = (it / C::kStages) & 1;
-                    const uint32_t ta = it % C::kAStages;
-                    const uint32_t ta_ph = (it / C::kAStages) & 1;
-                    mbar_wait(&bars->full[s], ph);      // token tile landed
-                    mbar_wait(&bars->a_full[ta], ta_ph); // weights are in TMEM
-                    tc_fence_after();
-                    const uint32_t act_addr =
-                        smem_u32(stage_base + (size_t)s * C::kStageBytes);
+                if (elect_one()) {
+                    const uint64_t bdesc_s = bdesc0 + (uint64_t)((s * C::kStageBytes) >> 4);
                     const uint32_t a_tmem = tmem_a0 + ta * C::kACols;
 #pragma unroll
                     for (int j = 0; j < KS / 16; ++j) {
-                        const uint64_t bdesc = make_smem_desc_sw128(
-                            act_addr + (j / 4) * (NTOK * 128) + (j % 4) * 32);
-                        mma_f16_ts(d_tmem, a_tmem + j * 8, bdesc, idesc,
-                                   (i | (uint32_t)j) != 0);
+                        constexpr int kDummy = 0;
+                        (void)kDummy;
+                        const uint64_t bdesc =
+                            bdesc_s + (uint64_t)(((j / 4) * (NTOK * 128) + (j % 4) * 32) >> 4);
+                        mma_f16_ts(d_tmem + (j % C::kChains) * NTOK, a_tmem + j * 8, bdesc,
+                                   idesc, (i != 0 || j >= C::kChains) ? 1u : 0u);
                     }
                     tc_commit(&bars->a_empty[ta]);
                     tc_commit(&bars->empty[s]);
+                    if (i + 1 == n_stage) tc_commit(&bars->acc_full[acc]);
                 }
-                tc_commit(&bars->acc_full[acc]);
-                u += g.kt1 - g.kt0;
+                __syncwarp();
             }
+            u += g.kt1 - g.kt0;
         }
     } else if (warp < kFirstEpilogueWarp) {
         // ===================== dequant warps =====================
@@ -259,6 +293,8 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
         const uint32_t row = quarter * 32 + lane;
         const uint32_t lane_base = (quarter * 32) << 16;
         constexpr int kMyChunks = C::kChunks / 2 > 0 ? C::kChunks / 2 : 1;
+        const uint32_t stage_base_u32 = smem_u32(stage_base);
+        const uint32_t two29 = args.two29;
         uint32_t it = 0;
         for (uint64_t u = u_begin; u < u_end;) {
             const Segment g = make_segment(sched, u, u_end);
@@ -270,9 +306,8 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                 const uint32_t ph = (it / C::kStages) & 1;
                 const uint32_t ta = it % C::kAStages;
                 const uint32_t ta_ph = (it / C::kAStages) & 1;
-                const uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
-                const uint8_t *wsm = st + C::kActBytes;
-                const uint8_t *scsm = wsm + C::kWBytes;
+                const uint32_t wsm = stage_base_u32 + s * C::kStageBytes + C::kActBytes;
+                const uint32_t scsm = wsm + C::kWBytes;
                 mbar_wait(&bars->full[s], ph);
                 // stage inputs -> registers
                 uint4 q[kMyChunks];
@@ -281,16 +316,13 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                 for (int ci = 0; ci < kMyChunks; ++ci) {
                     const int c = (C::kChunks >= 2) ? (int)khalf * kMyChunks + ci : 0;
                     if (active) {
-                        q[ci] = *reinterpret_cast<const uint4 *>(
-                            wsm + (size_t)c * rows * 16 + row * 16);
+                        q[ci] = lds_v4(wsm + (c * rows + row) * 16);
                         const int ksub = c / 2;
                         if (C::kIsMx) {
-                            uint32_t hw = *reinterpret_cast<const uint16_t *>(
-                                scsm + (size_t)ksub * rows * 2 + row * 2);
+                            uint32_t hw = lds_u16(scsm + (ksub * rows + row) * 2);
                             scw[ci] = (hw >> ((c & 1) * 8)) & 0xff;
                         } else {
-                            uint32_t w32 = *reinterpret_cast<const uint32_t *>(
-                                scsm + (size_t)ksub * rows * 4 + row * 4);
+                            uint32_t w32 = lds_u32(scsm + (ksub * rows + row) * 4);
                             scw[ci] = (w32 >> ((c & 1) * 16)) & 0xffff;
                         }
                     } else {
@@ -315,7 +347,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                             m1 = scale_multiplier<MODE>(scw[ci] >> 8, two1);
                         }
                         uint32_t out[16];
-                        dequant_chunk<MODE>(q[ci], m0, m1, two0, out);
+                        dequant_chunk<MODE>(q[ci], m0, m1, two0, two29, out);
                         tmem_st_x16(tmem_a0 + lane_base + ta * C::kACols + c * 16, out);
                     }
                 }
@@ -357,35 +389,42 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                 blockIdx.x * 2 + ((u == u_begin) ? 0u : 1u);
             float *slot = args.ws_partials + (size_t)my_slot * (kTileN * NTOK);
 
-            mbar_wait(&bars->acc_full[acc], acc_ph);
+            while (!mbar_try_wait(&bars->acc_full[acc], acc_ph)) __nanosleep(128);
             tc_fence_after();
 #pragma unroll 1
             for (int c0 = 0; c0 < NTOK; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld_x16(tmem + lane_base + acc * NTOK + c0, v);
-                tmem_wait_ld();
+                if ((uint32_t)c0 >= m_valid) break; // tokens beyond M are never stored
+                float v[16];
+                {
+                    uint32_t r0[16];
+                    tmem_ld_x16(tmem + lane_base + acc * C::kAccBufCols + c0, r0);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
+                }
+#pragma unroll
+                for (int ch = 1; ch < C::kChains; ++ch) {
+                    uint32_t r1[16];
+                    tmem_ld_x16(tmem + lane_base + acc * C::kAccBufCols + ch * NTOK + c0, r1);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
+                }
                 if (full_k) {
                     if (row_ok) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const uint32_t t = c0 + j;
-                            if (t < m_valid) {
-                                const float r = __uint_as_float(v[j]) * gs;
-                                const size_t off = (size_t)(m0 + t) * args.n + n_idx;
-                                if (C::kIsBf16)
-                                    reinterpret_cast<__nv_bfloat16 *>(args.c)[off] =
-                                        __float2bfloat16_rn(r);
-                                else
-                                    reinterpret_cast<__half *>(args.c)[off] =
-                                        __float2half_rn(r);
-                            }
+                            if (t < m_valid)
+                                store_out<C::kIsBf16>(args.c, (size_t)(m0 + t) * args.n + n_idx,
+                                                      v[j] * gs);
                         }
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        __stcg(&slot[(size_t)(c0 + j) * kTileN + row],
-                               __uint_as_float(v[j]));
+                        if ((uint32_t)(c0 + j) < m_valid)
+                            __stcg(&slot[(size_t)(c0 + j) * kTileN + row], v[j]);
                 }
             }
             // accumulator drained -> MMA may reuse it
@@ -404,27 +443,37 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                 const uint32_t old = bars->flag;
                 const uint32_t nseg = b_last - b_first + 1;
                 if (old == nseg - 1) {
-                    // last to arrive: reduce all partials in CTA order
+                    // last to arrive: reduce all partials in CTA order (deterministic)
                     __threadfence();
                     if (row_ok) {
+                        constexpr int kU = 8; // independent loads in flight per thread
 #pragma unroll 1
-                        for (uint32_t t = 0; t < m_valid; ++t) {
-                            float sum = 0.f;
+                        for (uint32_t t0 = 0; t0 < m_valid; t0 += kU) {
+                            float sum[kU];
+#pragma unroll
+                            for (int j = 0; j < kU; ++j) sum[j] = 0.f;
+#pragma unroll 1
                             for (uint32_t b = b_first; b <= b_last; ++b) {
                                 const uint64_t bu0 = sched.begin(b);
                                 const uint32_t sl =
                                     b * 2 + ((bu0 / sched.k_tiles) == g.tile ? 0u : 1u);
-                                sum += __ldcg(args.ws_partials +
-                                              (size_t)sl * (kTileN * NTOK) +
-                                              (size_t)t * kTileN + row);
+                                const float *p = args.ws_partials +
+                                                 (size_t)sl * (kTileN * NTOK) +
+                                                 (size_t)t0 * kTileN + row;
+                                float x[kU];
+#pragma unroll
+                                for (int j = 0; j < kU; ++j)
+                                    x[j] = (t0 + j < m_valid) ? __ldcg(p + (size_t)j * kTileN)
+                                                              : 0.f;
+#pragma unroll
+                                for (int j = 0; j < kU; ++j) sum[j] += x[j];
                             }
-                            const float r = sum * gs;
-                            const size_t off = (size_t)(m0 + t) * args.n + n_idx;
-                            if (C::kIsBf16)
-                                reinterpret_cast<__nv_bfloat16 *>(args.c)[off] =
-                                    __float2bfloat16_rn(r);
-                            else
-                                reinterpret_cast<__half *>(args.c)[off] = __float2half_rn(r);
+#pragma unroll
+                            for (int j = 0; j < kU; ++j)
+                                if (t0 + j < m_valid)
+                                    store_out<C::kIsBf16>(
+                                        args.c, (size_t)(m0 + t0 + j) * args.n + n_idx,
+                                        sum[j] * gs);
                         }
                     }
                     if (ew_tid == 0) args.ws_counters[g.tile] = 0; // self-cleaning
@@ -504,9 +553,9 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
 template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
                                     cudaStream_t stream) {
     switch (ntok) {
-    case 16: return launch_variant<MODE, 16, 256>(args, num_sms, stream);
-    case 32: return launch_variant<MODE, 32, 256>(args, num_sms, stream);
-    case 64: return launch_variant<MODE, 64, 256>(args, num_sms, stream);
+    case 16: return launch_variant<MODE, 16, 128>(args, num_sms, stream);
+    case 32: return launch_variant<MODE, 32, 128>(args, num_sms, stream);
+    case 64: return launch_variant<MODE, 64, 128>(args, num_sms, stream);
     case 128: return launch_variant<MODE, 128, 128>(args, num_sms, stream);
     case 256: return launch_variant<MODE, 256, 64>(args, num_sms, stream);
     default: return kLaunchNoKernel;

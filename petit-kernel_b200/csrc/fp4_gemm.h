@@ -22,6 +22,7 @@ struct GemmArgs {
     float *ws_partials;     // stream-K partial tiles
     unsigned *ws_counters;  // per-tile arrival counters (zero between launches)
     uint32_t m, n, k;
+    uint32_t two29;         // 1u << 29, passed at run time (see dequant.cuh)
 };
 
 size_t workspace_partials_bytes();

@@ -31,7 +31,7 @@ constexpr uint64_t kMfmaF16 = 0, kMfmaBf16 = 1;
 constexpr int kTokVariants[] = {16, 32, 64, 128, 256};
 constexpr int kNumVariants = 5;
 
-constexpr int stage_k_for(int ntok) { return ntok <= 64 ? 256 : (ntok == 128 ? 128 : 64); }
+constexpr int stage_k_for(int ntok) { return ntok <= 64 ? 256 : 128; }
 
 constexpr uint64_t make_solution(int ntok, uint64_t elem_b, uint64_t mfma) {
     return (uint64_t)(ntok / 16)                              // tile_m  [0,8)

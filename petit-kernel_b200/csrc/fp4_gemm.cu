@@ -23,7 +23,7 @@
 //    contiguous range per SM, so all 148 SMs stream the same number of bytes
 //    whatever the shape.  Tiles cut by a range boundary are reduced through an
 //    fp32 workspace by the last CTA to arrive, in a fixed order (bit-reproducible).
-//  * warp roles: 1 TMA producer, 1 MMA issuer, 8 dequant warps, 4 epilogue
+//  * warp roles: 1 TMA producer, 1 MMA issuer, 16 dequant warps, 4 epilogue
 //    warps; accumulators are double-buffered in TMEM so the epilogue overlaps
 //    the next tile.
 #include "fp4_gemm.h"
@@ -43,12 +43,20 @@ using namespace petit::dq;
 
 namespace {
 
-constexpr int kNumDequantWarps = 8;
+// Warp roles, aligned to warpgroups so setmaxnreg can rebalance registers:
+//   WG0: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-3 idle
+//   WG1: warps 4-7  = epilogue (one per TMEM lane quarter)
+//   WG2-5: warps 8-23 = dequant (4 per lane quarter -> 4 per SM sub-partition)
+constexpr int kNumDequantWarps = 16;
 constexpr int kNumEpilogueWarps = 4;
-constexpr int kFirstDequantWarp = 2;
-constexpr int kFirstEpilogueWarp = kFirstDequantWarp + kNumDequantWarps;
-constexpr int kNumWarps = kFirstEpilogueWarp + kNumEpilogueWarps;
+constexpr int kFirstEpilogueWarp = 4;
+constexpr int kFirstDequantWarp = 8;
+constexpr int kNumWarps = kFirstDequantWarp + kNumDequantWarps;
 constexpr int kNumThreads = kNumWarps * 32;
+constexpr int kKSlices = kNumDequantWarps / 4; // dequant warps per lane quarter
+// 768 threads x 80 registers = 61440 is the CTA pool setmaxnreg redistributes:
+// 128 x 40 (WG0) + 128 x 80 (epilogue) + 512 x 88 (dequant) = 60416 <= 61440.
+constexpr int kRegsLight = 40, kRegsDequant = 88;
 constexpr int kEpilogueBarId = 1;
 constexpr int kSmemBudget = 227 * 1024;
 
@@ -71,8 +79,9 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     // Small-N MMAs that accumulate into the same TMEM columns serialise on the
     // full MMA latency (~130 clk measured), so consecutive k-steps rotate over
     // kChains independent accumulators that the epilogue sums.
-    static constexpr int kChains = NTOK >= 128 ? 1 : 128 / NTOK;
-    static constexpr int kNumAcc = NTOK <= 128 ? 2 : 1;
+    static constexpr int kNumAcc = (NTOK <= 32 || NTOK == 128) ? 2 : 1;
+    static constexpr int kChains = NTOK >= 128 ? 1 : 128 / (kNumAcc * NTOK);
+    static_assert((KS / 32) % kKSlices == 0, "chunks must split evenly over the k-slices");
     static constexpr int kAccBufCols = kChains * NTOK;
     static constexpr int kAccCols = kNumAcc * kAccBufCols;
     static_assert(KS / 16 >= kChains, "stage must cover every accumulator chain");
@@ -99,15 +108,15 @@ static_assert(sizeof(Barriers) <= 1024, "barrier block too large");
 // Work decomposition shared by every warp role.
 struct Sched {
     uint32_t k_tiles, m_tiles, n_tiles;
-    uint64_t total_units;
+    uint32_t total_units; // < 2^31, checked by the launcher
     uint32_t grid;
 
-    __device__ __forceinline__ uint64_t begin(uint32_t b) const {
-        return total_units * b / grid;
+    __device__ __forceinline__ uint32_t begin(uint32_t b) const {
+        return (uint32_t)((uint64_t)total_units * b / grid);
     }
     // CTA that owns unit u (inverse of begin()).
-    __device__ __forceinline__ uint32_t owner(uint64_t u) const {
-        return (uint32_t)(((u + 1) * grid - 1) / total_units);
+    __device__ __forceinline__ uint32_t owner(uint32_t u) const {
+        return (uint32_t)((((uint64_t)u + 1) * grid - 1) / total_units);
     }
 };
 
@@ -115,19 +124,25 @@ struct Segment {
     uint32_t tile, n_tile, m_tile, kt0, kt1;
 };
 
-__device__ __forceinline__ Segment make_segment(const Sched &s, uint64_t u,
-                                                uint64_t u_end) {
+__device__ __forceinline__ Segment make_segment(const Sched &s, uint32_t u,
+                                                uint32_t u_end) {
     Segment g;
-    g.tile = (uint32_t)(u / s.k_tiles);
-    g.kt0 = (uint32_t)(u % s.k_tiles);
-    uint64_t left = u_end - u;
+    g.tile = u / s.k_tiles;
+    g.kt0 = u - g.tile * s.k_tiles;
+    uint32_t left = u_end - u;
     uint32_t room = s.k_tiles - g.kt0;
-    g.kt1 = g.kt0 + (uint32_t)(left < room ? left : room);
+    g.kt1 = g.kt0 + (left < room ? left : room);
     g.n_tile = g.tile / s.m_tiles;
     g.m_tile = g.tile % s.m_tiles;
     return g;
 }
 
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -173,10 +188,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
     sched.k_tiles = args.k / kTileK;
     sched.n_tiles = (args.n + kTileN - 1) / kTileN;
     sched.m_tiles = (args.m + NTOK - 1) / NTOK;
-    sched.total_units = (uint64_t)sched.k_tiles * sched.n_tiles * sched.m_tiles;
+    sched.total_units = sched.k_tiles * sched.n_tiles * sched.m_tiles;
     sched.grid = gridDim.x;
-    const uint64_t u_begin = sched.begin(blockIdx.x);
-    const uint64_t u_end = sched.begin(blockIdx.x + 1);
+    const uint32_t u_begin = sched.begin(blockIdx.x);
+    const uint32_t u_end = sched.begin(blockIdx.x + 1);
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmap_act);
@@ -203,13 +218,14 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
 
     const uint32_t k_bytes_half = args.k / 2;
 
+    if (warp < kFirstEpilogueWarp) setmaxnreg_dec<kRegsLight>();
     if (warp == 0) {
         // ===================== TMA producer =====================
         // The loop is executed by the whole (converged) warp so that every value is
         // warp-uniform; only the async instructions are issued by one elected lane.
         const uint64_t pol_stream = policy_evict_first();
         uint32_t it = 0;
-        for (uint64_t u = u_begin; u < u_end;) {
+        for (uint32_t u = u_begin; u < u_end;) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t rows = tile_rows(args.n, g.n_tile);
             const uint8_t *w_tile = args.w + (size_t)g.n_tile * kTileN * k_bytes_half;
@@ -249,7 +265,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             C::kIsBf16 ? kFmtBF16 : kFmtF16, C::kIsBf16 ? kFmtBF16 : kFmtF16, 128, NTOK);
         const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(stage_base));
         uint32_t it = 0, seg = 0;
-        for (uint64_t u = u_begin; u < u_end; ++seg) {
+        for (uint32_t u = u_begin; u < u_end; ++seg) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t acc = seg % C::kNumAcc;
             const uint32_t acc_ph = (seg / C::kNumAcc) & 1;
@@ -285,18 +301,19 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             }
             u += g.kt1 - g.kt0;
         }
-    } else if (warp < kFirstEpilogueWarp) {
+    } else if (warp >= kFirstDequantWarp) {
         // ===================== dequant warps =====================
+        setmaxnreg_inc<kRegsDequant>();
         const uint32_t dw = warp - kFirstDequantWarp;
         const uint32_t quarter = warp % 4;     // TMEM lane quarter this warp may touch
-        const uint32_t khalf = dw / 4;         // which half of the stage's k range
+        const uint32_t khalf = dw / 4;         // which slice of the stage's k range
         const uint32_t row = quarter * 32 + lane;
         const uint32_t lane_base = (quarter * 32) << 16;
-        constexpr int kMyChunks = C::kChunks / 2 > 0 ? C::kChunks / 2 : 1;
+        constexpr int kMyChunks = C::kChunks / kKSlices;
         const uint32_t stage_base_u32 = smem_u32(stage_base);
         const uint32_t two29 = args.two29;
         uint32_t it = 0;
-        for (uint64_t u = u_begin; u < u_end;) {
+        for (uint32_t u = u_begin; u < u_end;) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t rows = tile_rows(args.n, g.n_tile);
             const bool active = row < rows;
@@ -314,7 +331,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                 uint32_t scw[kMyChunks];
 #pragma unroll
                 for (int ci = 0; ci < kMyChunks; ++ci) {
-                    const int c = (C::kChunks >= 2) ? (int)khalf * kMyChunks + ci : 0;
+                    const int c = (int)khalf * kMyChunks + ci;
                     if (active) {
                         q[ci] = lds_v4(wsm + (c * rows + row) * 16);
                         const int ksub = c / 2;
@@ -333,10 +350,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                 // the previous occupant of this TMEM A stage must have been consumed
                 mbar_wait(&bars->a_empty[ta], ta_ph ^ 1);
                 tc_fence_after();
-                if (C::kChunks >= 2 || khalf == 0) {
+                {
 #pragma unroll
                     for (int ci = 0; ci < kMyChunks; ++ci) {
-                        const int c = (C::kChunks >= 2) ? (int)khalf * kMyChunks + ci : 0;
+                        const int c = (int)khalf * kMyChunks + ci;
                         bool two0 = false, two1 = false;
                         uint32_t m0, m1;
                         if (C::kIsMx) {
@@ -361,7 +378,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             }
             u += g.kt1 - g.kt0;
         }
-    } else {
+    } else if (warp >= kFirstEpilogueWarp) {
         // ===================== epilogue warps =====================
         const uint32_t quarter = warp % 4;
         const uint32_t ew_tid = threadIdx.x - kFirstEpilogueWarp * 32; // 0..127
@@ -370,7 +387,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
         float gs = *args.global_scale;
         gs *= epilogue_factor<MODE>(); // power of two folded out of the MX multiplier
         uint32_t seg = 0;
-        for (uint64_t u = u_begin; u < u_end; ++seg) {
+        for (uint32_t u = u_begin; u < u_end; ++seg) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t rows = tile_rows(args.n, g.n_tile);
             const uint32_t acc = seg % C::kNumAcc;
@@ -382,7 +399,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             const bool row_ok = row < rows;
 
             // partial-tile bookkeeping
-            const uint64_t tile_u0 = (uint64_t)g.tile * sched.k_tiles;
+            const uint32_t tile_u0 = g.tile * sched.k_tiles;
             const uint32_t b_first = sched.owner(tile_u0);
             const uint32_t b_last = sched.owner(tile_u0 + sched.k_tiles - 1);
             const uint32_t my_slot =
@@ -454,7 +471,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                             for (int j = 0; j < kU; ++j) sum[j] = 0.f;
 #pragma unroll 1
                             for (uint32_t b = b_first; b <= b_last; ++b) {
-                                const uint64_t bu0 = sched.begin(b);
+                                const uint32_t bu0 = sched.begin(b);
                                 const uint32_t sl =
                                     b * 2 + ((bu0 / sched.k_tiles) == g.tile ? 0u : 1u);
                                 const float *p = args.ws_partials +
@@ -545,7 +562,8 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     const uint64_t m_tiles = (args.m + NTOK - 1) / NTOK;
     const uint64_t units = n_tiles * m_tiles * (args.k / kTileK);
     const unsigned grid = (unsigned)(units < (uint64_t)num_sms ? units : (uint64_t)num_sms);
-    if (m_tiles * n_tiles > kMaxTiles || grid > kMaxGrid) return kLaunchBadShape;
+    if (m_tiles * n_tiles > kMaxTiles || grid > kMaxGrid || units >= (1ull << 31))
+        return kLaunchBadShape;
     kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmap, args);
     return cudaGetLastError() == cudaSuccess ? kLaunchOk : kLaunchCudaError;
 }
@@ -553,11 +571,11 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
 template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
                                     cudaStream_t stream) {
     switch (ntok) {
-    case 16: return launch_variant<MODE, 16, 128>(args, num_sms, stream);
-    case 32: return launch_variant<MODE, 32, 128>(args, num_sms, stream);
-    case 64: return launch_variant<MODE, 64, 128>(args, num_sms, stream);
+    case 16: return launch_variant<MODE, 16, 256>(args, num_sms, stream);
+    case 32: return launch_variant<MODE, 32, 256>(args, num_sms, stream);
+    case 64: return launch_variant<MODE, 64, 256>(args, num_sms, stream);
     case 128: return launch_variant<MODE, 128, 128>(args, num_sms, stream);
-    case 256: return launch_variant<MODE, 256, 64>(args, num_sms, stream);
+    case 256: return launch_variant<MODE, 256, 128>(args, num_sms, stream);
     default: return kLaunchNoKernel;
     }
 }

@@ -58,6 +58,7 @@ constexpr int kKSlices = kNumDequantWarps / 4; // dequant warps per lane quarter
 // 128 x 40 (WG0) + 128 x 80 (epilogue) + 512 x 88 (dequant) = 60416 <= 61440.
 constexpr int kRegsLight = 40, kRegsDequant = 88;
 constexpr int kEpilogueBarId = 1;
+constexpr int kSetupBarId = 2;
 constexpr int kSmemBudget = 227 * 1024;
 
 template <int MODE, int NTOK, int KS> struct Cfg {
@@ -137,6 +138,13 @@ __device__ __forceinline__ Segment make_segment(const Sched &s, uint32_t u,
     return g;
 }
 
+__device__ __forceinline__ void trace_stamp(const GemmArgs &args, int slot) {
+    if (args.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        args.trace[blockIdx.x * 16 + slot] = t;
+    }
+}
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
@@ -153,6 +161,11 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
@@ -183,6 +196,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
     uint8_t *stage_base = smem + C::kBarrierBytes;
 
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (threadIdx.x == 0) trace_stamp(args, 0);
 
     Sched sched;
     sched.k_tiles = args.k / kTileK;
@@ -211,10 +225,18 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
     }
     if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
     tc_fence_before();
-    __syncthreads();
+    // Warp 0 initialised the barriers itself, so it only signals the setup barrier
+    // and starts streaming weights while the other warps wait for the TMEM base.
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("bar.arrive %0, %1;" ::"n"(kSetupBarId), "n"(kNumThreads) : "memory");
+    } else {
+        named_bar_sync(kSetupBarId, kNumThreads);
+    }
     tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem = warp == 0 ? 0u : bars->tmem_base;
     const uint32_t tmem_a0 = tmem + C::kAccCols;
+    if (threadIdx.x == 0) trace_stamp(args, 1);
 
     const uint32_t k_bytes_half = args.k / 2;
 
@@ -251,6 +273,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                                   &bars->full[s], pol_stream);
                     // token tile: box {64 k, NTOK tokens, kSubs slabs}
                     tma_load_3d(st, &tmap_act, &bars->full[s], 0, g.m_tile * NTOK, k_slab);
+                    if (it == 0) trace_stamp(args, 2);
                 }
                 __syncwarp();
                 w_src += w_stage_bytes;
@@ -301,72 +324,57 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             }
             u += g.kt1 - g.kt0;
         }
+        if (lane == 0) trace_stamp(args, 5);
     } else if (warp >= kFirstDequantWarp) {
         // ===================== dequant warps =====================
         setmaxnreg_inc<kRegsDequant>();
         const uint32_t dw = warp - kFirstDequantWarp;
         const uint32_t quarter = warp % 4;     // TMEM lane quarter this warp may touch
-        const uint32_t khalf = dw / 4;         // which slice of the stage's k range
+        const uint32_t kslice = dw / 4;        // which slice of the stage's k range
         const uint32_t row = quarter * 32 + lane;
-        const uint32_t lane_base = (quarter * 32) << 16;
         constexpr int kMyChunks = C::kChunks / kKSlices;
-        const uint32_t stage_base_u32 = smem_u32(stage_base);
-        const uint32_t two29 = args.two29;
-        uint32_t it = 0;
+        constexpr int kScBytesPerChunk = C::kScPerSub / 2; // NV: 2 bytes, MX: 1 byte
+        constexpr int kMyScBytes = kMyChunks * kScBytesPerChunk;
+        const uint32_t c0 = kslice * kMyChunks;            // first chunk of this thread
+        const uint32_t w_base = smem_u32(stage_base) + C::kActBytes;
+        const uint32_t tmem_dst = tmem_a0 + ((quarter * 32) << 16) + c0 * 16;
+        const Consts dc = {args.two29, args.add64};
+        uint32_t s = 0, ph = 0, ta = 0, ta_ph = 1; // ta_ph: parity to wait on a_empty
+        bool first = true;
         for (uint32_t u = u_begin; u < u_end;) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t rows = tile_rows(args.n, g.n_tile);
-            const bool active = row < rows;
+            // rows past the end of a cut n-tile re-read the last valid row: their
+            // accumulator lanes are never stored, and no predication is needed.
+            const uint32_t rrow = row < rows ? row : rows - 1;
+            const uint32_t w_off = (c0 * rows + rrow) * 16;
+            const uint32_t sc_off = C::kWBytes + ((c0 / 2) * rows + rrow) * C::kScPerSub +
+                                    (c0 & 1) * kScBytesPerChunk;
             const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
-            for (uint32_t i = 0; i < n_stage; ++i, ++it) {
-                const uint32_t s = it % C::kStages;
-                const uint32_t ph = (it / C::kStages) & 1;
-                const uint32_t ta = it % C::kAStages;
-                const uint32_t ta_ph = (it / C::kAStages) & 1;
-                const uint32_t wsm = stage_base_u32 + s * C::kStageBytes + C::kActBytes;
-                const uint32_t scsm = wsm + C::kWBytes;
+            for (uint32_t i = 0; i < n_stage; ++i) {
+                const uint32_t st = w_base + s * C::kStageBytes;
                 mbar_wait(&bars->full[s], ph);
-                // stage inputs -> registers
+                if (first && threadIdx.x == kFirstDequantWarp * 32) trace_stamp(args, 3);
+                first = false;
                 uint4 q[kMyChunks];
-                uint32_t scw[kMyChunks];
+#pragma unroll
+                for (int ci = 0; ci < kMyChunks; ++ci) q[ci] = lds_v4(st + w_off + ci * rows * 16);
+                uint32_t scbits;
+                if (kMyScBytes == 4) scbits = lds_u32(st + sc_off);
+                else if (kMyScBytes == 2) scbits = lds_u16(st + sc_off);
+                else scbits = lds_u8(st + sc_off);
+                // the previous occupant of this TMEM A stage must have been consumed
+                mbar_wait(&bars->a_empty[ta], ta_ph);
+                tc_fence_after();
 #pragma unroll
                 for (int ci = 0; ci < kMyChunks; ++ci) {
-                    const int c = (int)khalf * kMyChunks + ci;
-                    if (active) {
-                        q[ci] = lds_v4(wsm + (c * rows + row) * 16);
-                        const int ksub = c / 2;
-                        if (C::kIsMx) {
-                            uint32_t hw = lds_u16(scsm + (ksub * rows + row) * 2);
-                            scw[ci] = (hw >> ((c & 1) * 8)) & 0xff;
-                        } else {
-                            uint32_t w32 = lds_u32(scsm + (ksub * rows + row) * 4);
-                            scw[ci] = (w32 >> ((c & 1) * 16)) & 0xffff;
-                        }
-                    } else {
-                        q[ci] = make_uint4(0, 0, 0, 0);
-                        scw[ci] = 0;
-                    }
-                }
-                // the previous occupant of this TMEM A stage must have been consumed
-                mbar_wait(&bars->a_empty[ta], ta_ph ^ 1);
-                tc_fence_after();
-                {
-#pragma unroll
-                    for (int ci = 0; ci < kMyChunks; ++ci) {
-                        const int c = (int)khalf * kMyChunks + ci;
-                        bool two0 = false, two1 = false;
-                        uint32_t m0, m1;
-                        if (C::kIsMx) {
-                            m0 = scale_multiplier<MODE>(scw[ci], two0);
-                            m1 = m0;
-                        } else {
-                            m0 = scale_multiplier<MODE>(scw[ci] & 0xff, two0);
-                            m1 = scale_multiplier<MODE>(scw[ci] >> 8, two1);
-                        }
-                        uint32_t out[16];
-                        dequant_chunk<MODE>(q[ci], m0, m1, two0, two29, out);
-                        tmem_st_x16(tmem_a0 + lane_base + ta * C::kACols + c * 16, out);
-                    }
+                    const uint32_t bits = scbits >> (ci * 8 * kScBytesPerChunk);
+                    bool two_step = false;
+                    if (C::kIsMx) two_step = __any_sync(0xffffffffu, mx_needs_two_step(bits));
+                    const uint32_t mult = chunk_multiplier<MODE>(bits, two_step);
+                    uint32_t out[16];
+                    dequant_chunk<MODE>(q[ci], mult, two_step, dc, out);
+                    tmem_st_x16(tmem_dst + ta * C::kACols + ci * 16, out);
                 }
                 tmem_wait_st();
                 tc_fence_before();
@@ -375,9 +383,12 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                     mbar_arrive(&bars->a_full[ta]);
                     mbar_arrive(&bars->empty[s]);
                 }
+                if (++s == C::kStages) { s = 0; ph ^= 1; }
+                if (++ta == C::kAStages) { ta = 0; ta_ph ^= 1; }
             }
             u += g.kt1 - g.kt0;
         }
+        if (threadIdx.x == kFirstDequantWarp * 32) trace_stamp(args, 4);
     } else if (warp >= kFirstEpilogueWarp) {
         // ===================== epilogue warps =====================
         const uint32_t quarter = warp % 4;
@@ -408,6 +419,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
 
             while (!mbar_try_wait(&bars->acc_full[acc], acc_ph)) __nanosleep(128);
             tc_fence_after();
+            if (ew_tid == 0 && u + (g.kt1 - g.kt0) >= u_end) trace_stamp(args, 6);
 #pragma unroll 1
             for (int c0 = 0; c0 < NTOK; c0 += 16) {
                 if ((uint32_t)c0 >= m_valid) break; // tokens beyond M are never stored
@@ -450,40 +462,54 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
 
             if (!full_k) {
-                __threadfence();
+                // publish the partial: CTA barrier, then one release-atomic on the tile
+                // counter (cumulative over the barrier); the last CTA to arrive acquires.
                 named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
                 if (ew_tid == 0) {
-                    const uint32_t old = atomicAdd(&args.ws_counters[g.tile], 1u);
+                    uint32_t old;
+                    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;"
+                                 : "=r"(old)
+                                 : "l"(args.ws_counters + g.tile)
+                                 : "memory");
                     bars->flag = old;
                 }
                 named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
                 const uint32_t old = bars->flag;
                 const uint32_t nseg = b_last - b_first + 1;
                 if (old == nseg - 1) {
-                    // last to arrive: reduce all partials in CTA order (deterministic)
-                    __threadfence();
+                    // last to arrive: reduce all partials in CTA order (deterministic).
+                    // All loads of a pass are issued before the first add so the pass
+                    // costs one L2 round trip.
                     if (row_ok) {
-                        constexpr int kU = 8; // independent loads in flight per thread
+                        constexpr int kU = 8, kSeg = 4;
 #pragma unroll 1
                         for (uint32_t t0 = 0; t0 < m_valid; t0 += kU) {
                             float sum[kU];
 #pragma unroll
                             for (int j = 0; j < kU; ++j) sum[j] = 0.f;
 #pragma unroll 1
-                            for (uint32_t b = b_first; b <= b_last; ++b) {
-                                const uint32_t bu0 = sched.begin(b);
-                                const uint32_t sl =
-                                    b * 2 + ((bu0 / sched.k_tiles) == g.tile ? 0u : 1u);
-                                const float *p = args.ws_partials +
-                                                 (size_t)sl * (kTileN * NTOK) +
-                                                 (size_t)t0 * kTileN + row;
-                                float x[kU];
+                            for (uint32_t bb = b_first; bb <= b_last; bb += kSeg) {
+                                float x[kSeg][kU];
 #pragma unroll
-                                for (int j = 0; j < kU; ++j)
-                                    x[j] = (t0 + j < m_valid) ? __ldcg(p + (size_t)j * kTileN)
-                                                              : 0.f;
+                                for (int sg = 0; sg < kSeg; ++sg) {
+                                    const uint32_t b = bb + sg;
+                                    const bool seg_ok = b <= b_last;
+                                    const uint32_t bc = seg_ok ? b : b_last;
+                                    const uint32_t sl =
+                                        bc * 2 + ((sched.begin(bc) / sched.k_tiles) == g.tile ? 0u : 1u);
+                                    const float *p = args.ws_partials +
+                                                     (size_t)sl * (kTileN * NTOK) +
+                                                     (size_t)t0 * kTileN + row;
 #pragma unroll
-                                for (int j = 0; j < kU; ++j) sum[j] += x[j];
+                                    for (int j = 0; j < kU; ++j)
+                                        x[sg][j] = (seg_ok && t0 + j < m_valid)
+                                                       ? __ldcg(p + (size_t)j * kTileN)
+                                                       : 0.f;
+                                }
+#pragma unroll
+                                for (int sg = 0; sg < kSeg; ++sg)
+#pragma unroll
+                                    for (int j = 0; j < kU; ++j) sum[j] += x[sg][j];
                             }
 #pragma unroll
                             for (int j = 0; j < kU; ++j)
@@ -502,8 +528,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
         }
     }
 
+    if (threadIdx.x == kFirstEpilogueWarp * 32) trace_stamp(args, 7);
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) trace_stamp(args, 8);
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 

@@ -23,6 +23,8 @@ struct GemmArgs {
     unsigned *ws_counters;  // per-tile arrival counters (zero between launches)
     uint32_t m, n, k;
     uint32_t two29;         // 1u << 29, passed at run time (see dequant.cuh)
+    unsigned long long add64; // 0x70007000ull << 32, same reason
+    unsigned long long *trace; // optional [grid][16] globaltimer stamps (debug), else null
 };
 
 size_t workspace_partials_bytes();

@@ -83,7 +83,7 @@ template <int MODE, bool kPacked>
 __global__ void __launch_bounds__(kThreads)
 dequant_dense_kernel(uint32_t *__restrict__ out, const uint8_t *__restrict__ w,
                      const uint8_t *__restrict__ sc, float global_scale, uint32_t size_n,
-                     uint32_t size_k, uint32_t two29) {
+                     uint32_t size_k, uint32_t two29, unsigned long long add64) {
     constexpr bool kIsMx = MODE == gemm::kModeMxBf16;
     constexpr bool kIsBf16 = MODE != gemm::kModeNvF16;
     constexpr uint32_t kGroup = kIsMx ? 32 : 16;
@@ -118,11 +118,12 @@ dequant_dense_kernel(uint32_t *__restrict__ out, const uint8_t *__restrict__ w,
             s0 = kIsMx ? sc[so] : e4m3_to_e5m3(sc[so]);
             s1 = kIsMx ? s0 : e4m3_to_e5m3(sc[so + 1]);
         }
-        bool two0 = false, two1 = false;
-        const uint32_t m0 = dq::scale_multiplier<MODE>(s0, two0);
-        const uint32_t m1 = kIsMx ? m0 : dq::scale_multiplier<MODE>(s1, two1);
+        const uint32_t bits = kIsMx ? s0 : (s0 | (s1 << 8));
+        const bool two_step = kIsMx && dq::mx_needs_two_step(bits);
+        const uint32_t mult = dq::chunk_multiplier<MODE>(bits, two_step);
+        const dq::Consts dc = {two29, add64};
         uint32_t v[16];
-        dq::dequant_chunk<MODE>(q, m0, m1, two0, two29, v);
+        dq::dequant_chunk<MODE>(q, mult, two_step, dc, v);
         uint32_t *dst = out + ((size_t)n * size_k + k0) / 2;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -189,10 +190,10 @@ int dequant_dense(void *out, const void *w, const void *sc, float global_scale, 
 #define PETIT_DQ(MODE)                                                                        \
     if (packed)                                                                               \
         dequant_dense_kernel<MODE, true>                                                      \
-            <<<g, kThreads, 0, stream>>>(o, wp, sp, global_scale, size_n, size_k, 1u << 29); \
+            <<<g, kThreads, 0, stream>>>(o, wp, sp, global_scale, size_n, size_k, 1u << 29, 0x70007000ull << 32); \
     else                                                                                      \
         dequant_dense_kernel<MODE, false>                                                     \
-            <<<g, kThreads, 0, stream>>>(o, wp, sp, global_scale, size_n, size_k, 1u << 29);
+            <<<g, kThreads, 0, stream>>>(o, wp, sp, global_scale, size_n, size_k, 1u << 29, 0x70007000ull << 32);
     switch (mode) {
     case gemm::kModeNvF16: PETIT_DQ(gemm::kModeNvF16) break;
     case gemm::kModeNvBf16: PETIT_DQ(gemm::kModeNvBf16) break;

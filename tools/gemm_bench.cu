@@ -28,6 +28,8 @@ __global__ void fill_kernel(uint32_t *p, size_t n, uint32_t seed, uint32_t mask,
     }
 }
 
+extern "C" void petit_debug_set_trace(unsigned long long *);
+
 int main(int argc, char **argv) {
     bool mx = argc > 1 && !strcmp(argv[1], "mx");
     bool bf16 = !(argc > 2 && !strcmp(argv[2], "f16"));
@@ -87,6 +89,34 @@ int main(int argc, char **argv) {
             float ms_total;
             cudaEventElapsedTime(&ms_total, e0, e1);
             double us = ms_total * 1e3 / r;
+            if (getenv("PETIT_TRACE")) {
+                unsigned long long *d_tr;
+                CK(cudaMalloc(&d_tr, 160 * 16 * 8));
+                CK(cudaMemset(d_tr, 0, 160 * 16 * 8));
+                petit_debug_set_trace(d_tr);
+                call(1);
+                CK(cudaDeviceSynchronize());
+                petit_debug_set_trace(nullptr);
+                std::vector<unsigned long long> tr(160 * 16);
+                CK(cudaMemcpy(tr.data(), d_tr, tr.size() * 8, cudaMemcpyDeviceToHost));
+                unsigned long long t0 = ~0ull;
+                int nb = 0;
+                for (int b = 0; b < 160; ++b) if (tr[b * 16]) { t0 = std::min(t0, tr[b * 16]); ++nb; }
+                const char *names[9] = {"entry", "setup_done", "first_tma_issued", "first_stage_landed",
+                                        "dequant_done", "mma_issued_all", "last_acc_full", "epilogue_done", "exit"};
+                printf("  trace over %d CTAs (us since first CTA entry): event min/avg/max\n", nb);
+                for (int e = 0; e < 9; ++e) {
+                    double mn = 1e30, mx2 = 0, sum = 0; int cnt = 0;
+                    for (int b = 0; b < 160; ++b) {
+                        unsigned long long v = tr[b * 16 + e];
+                        if (!v || !tr[b * 16]) continue;
+                        double d = (double)(v - t0) * 1e-3;
+                        mn = std::min(mn, d); mx2 = std::max(mx2, d); sum += d; ++cnt;
+                    }
+                    if (cnt) printf("    %-20s %7.2f %7.2f %7.2f\n", names[e], mn, sum / cnt, mx2);
+                }
+                cudaFree(d_tr);
+            }
             double bytes = (double)wbytes + sbytes + 2.0 * m * s.k + 2.0 * m * s.n + 4;
             double flops = 2.0 * m * s.n * s.k;
             printf("%-7s %s %s M=%-5u  %9.2f us  %7.0f GB/s (%5.1f%% of %.0f)  %7.1f TFLOPS (%5.1f%% of %.0f)\n",

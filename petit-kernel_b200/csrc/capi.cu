@@ -180,6 +180,13 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
     args.two29 = 1u << 29;
     args.add64 = 0x70007000ull << 32;
     args.trace = g_trace;
+    {
+        static const int skew = [] {
+            const char *e = std::getenv("PETIT_SKEW");
+            return e ? std::atoi(e) : 0;
+        }();
+        args.skew_cycles = (uint32_t)skew;
+    }
     const int mode = d.elem_b == kElemMx
                          ? gemm::kModeMxBf16
                          : (d.mfma == kMfmaBf16 ? gemm::kModeNvBf16 : gemm::kModeNvF16);

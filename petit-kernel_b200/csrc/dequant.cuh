@@ -6,16 +6,20 @@
 // (lib/gemm/rocm/quantization/dequant.cuh:38-401).  Contract kept: every
 // dequantised weight e2m1 * scale is produced EXACTLY (<= 6 significant bits).
 //
-// Instruction budget (measured on B200, profiles/r01_probe_hw_facts.log): the ALU
-// pipe (F2FP, LOP3, SHF, PRMT, LEA; 64 lanes/clk/SM) is the decode bottleneck, so
-// everything that can run on the FMA pipe does:
-//   NVFP4 -> fp16 : F2FP (ALU) + HMUL2 (FMA)                      per 2 weights
-//   NVFP4 -> bf16 : F2FP (ALU) + IMAD.HI (FMA) + LOP3 (ALU) + HMUL2.BF16 (FMA)
-//   MXFP4 -> bf16 : as NVFP4 -> bf16 (+ one HMUL2.BF16 for scales >= 2^14)
+// The e2m1 code [s e1 e0 m] dropped into a 16-bit float with its sign at bit 15 and
+// e1 e0 m at the two lowest exponent bits + top mantissa bit IS the value scaled by
+// a power of two, subnormal and zero included:
+//     bf16: bits [8:6]   -> value * 2^-126        fp16: bits [11:9] -> value * 2^-14
+// layout.cuh::pack_word stores the bits of a word so that these patterns fall out
+// with one shift/rotate + one LOP3 per PAIR of weights for bf16; HMUL2 by the block
+// scale (times the inverse power of two) then normalises and scales in one exact
+// step.  Instruction budget per 2 weights (B200: the 64-lane/clk ALU pipe is the
+// decode bottleneck, see profiles/):
+//     bf16: 1.75 ALU (LOP3, SHF) + 1.5 FMA-pipe (IMAD.SHL, HMUL2.BF16)
+//     fp16: 2.75 ALU            + 2.5 FMA-pipe
 #pragma once
 
 #include "fp4_gemm.h"
-#include "sm100_ptx.cuh"
 
 #include <cstdint>
 #include <cuda_bf16.h>
@@ -26,14 +30,6 @@ namespace petit::dq {
 using petit::gemm::kModeMxBf16;
 using petit::gemm::kModeNvBf16;
 using petit::gemm::kModeNvF16;
-using petit::ptx::cvt_e2m1x8_to_f16x2x4;
-
-// Run-time constants that must not be visible to ptxas as immediates (it would
-// strength-reduce the multiply-high back into ALU-pipe shifts).
-struct Consts {
-    uint32_t two29;  // 1 << 29
-    uint64_t add64;  // 0x70007000 << 32
-};
 
 __device__ __forceinline__ uint32_t hmul2_f16(uint32_t a, uint32_t b) {
     uint32_t d;
@@ -63,77 +59,87 @@ __device__ __forceinline__ uint32_t hmul2_bcast(uint32_t a, uint32_t s) {
     }
 }
 
-// f16x2 bits of a normal-or-zero value with <= 7 mantissa bits -> bf16x2 bits of
-// (value * 2^-112): shift exponent+mantissa down by 3 (IMAD.HI by 2^29) and move
-// the sign from bit 12 back to bit 15 (the 0x7000 addend carries it up, the mask
-// drops the carry trail).
-__device__ __forceinline__ uint32_t f16x2_to_bf16x2_scaled(uint32_t h, const Consts &c) {
-    const uint64_t p = (uint64_t)h * c.two29 + c.add64;
-    return (uint32_t)(p >> 32) & 0x8fff8fffu;
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) {
+    return __funnelshift_l(x, x, r);
 }
 
-// Scale bits of one 32-weight chunk -> multiplier register.
-//   NVFP4: `bits` = two E5M3 bytes (groups of 16); result = (mult0, mult1) halves.
-//   MXFP4: `bits` = one e8m0 byte; result = same multiplier in both halves.
-//          `two_step` (must be true when mx_needs_two_step(bits); may be forced true,
-//          e.g. warp-uniformly) selects the form with the extra * 2^112.
-__device__ __forceinline__ bool mx_needs_two_step(uint32_t bits) { return (bits & 0xff) > 140; }
+// One packed word (8 weights) -> 4 bf16x2 registers holding value * 2^-126.
+__device__ __forceinline__ void extract_bf16(uint32_t q, uint32_t (&x)[4]) {
+    constexpr uint32_t kM = 0x81c081c0u;
+    x[0] = q & kM;
+    x[1] = (q << 4) & kM;
+    x[2] = rotl32(q, 10) & kM;
+    x[3] = (rotl32(q, 14) & 0x81808180u) | ((q << 6) & 0x00400040u);
+}
+// One packed word -> 4 f16x2 registers holding value * 2^-14.
+__device__ __forceinline__ void extract_f16(uint32_t q, uint32_t (&x)[4]) {
+    constexpr uint32_t kS = 0x80008000u, kG = 0x0e000e00u;
+    x[0] = ((q << 3) & kG) | (q & kS);
+    x[1] = ((q << 7) & kG) | ((q << 4) & kS);
+    x[2] = (rotl32(q, 13) & kG) | ((q << 10) & kS);
+    x[3] = (rotl32(q, 17) & 0x0c000c00u) | ((q << 9) & 0x02000200u) | ((q << 14) & kS);
+}
 
+// Power of two folded out of the A operand and applied in the epilogue: the A
+// operand holds  w * 2^-8 (NVFP4 bf16),  w * 2^-7 (NVFP4 fp16)  or  w * 4 (MXFP4).
+template <int MODE> __host__ __device__ constexpr float epilogue_factor() {
+    return MODE == kModeMxBf16 ? 0.25f : (MODE == kModeNvBf16 ? 256.0f : 128.0f);
+}
+
+__device__ __forceinline__ bool mx_needs_two_step(uint32_t bits) { return (bits & 0xff) > 125; }
+
+// Scale bits of one 32-weight chunk -> multiplier register.
+//   NVFP4: `bits` = two E5M3 bytes (groups of 16); result = (mult0, mult1) halves,
+//          mult = scale * 2^118 (bf16) / scale * 2^7 (fp16); a zero byte gives 0.
+//   MXFP4: `bits` = one e8m0 byte s; result = 2^(s+1) in both halves, or, when
+//          `two_step` (required if mx_needs_two_step; may be forced warp-uniformly),
+//          2^(s-125) to be applied after an exact * 2^126.
 template <int MODE>
 __device__ __forceinline__ uint32_t chunk_multiplier(uint32_t bits, bool two_step) {
     if (MODE == kModeMxBf16) {
-        // A operand holds w * 4:  one step 2^(s-13) (field s+114) when representable,
-        // else (t * 2^112) * 2^(s-125) (field s+2).
         const uint32_t s = bits & 0xff;
-        uint32_t field = two_step ? s + 2 : s + 114;
+        uint32_t field = two_step ? s + 2 : s + 128;
         field = field > 255 ? 255 : field;
         return field * 0x00800080u;
     }
-    // bytes (b0, b1) -> 16-bit lanes
-    const uint32_t x = __byte_perm(bits, 0, 0x4140);
+    const uint32_t x = __byte_perm(bits, 0, 0x4140);     // bytes (b0, b1) -> 16-bit lanes
+    const uint32_t nz = (x + 0x00ff00ffu) & 0x01000100u; // bit 8 of a lane = (byte != 0)
     if (MODE == kModeNvF16) {
-        // E5M3 byte == fp16 exponent + top 3 mantissa bits: bits [14:7]
-        return x << 7;
+        // fp16(scale * 2^7): exponent field e5 + 7, top 3 mantissa bits = m
+        return x * 128u + nz * 0x1cu;
     }
-    // bf16 bits of scale * 2^112: (byte << 4) + (224 << 7); a zero byte stays zero
-    const uint32_t nz = (x + 0x00ff00ffu) & 0x01000100u; // bit 8 of each lane = (byte != 0)
-    return x * 16u + nz * 0x70u;
+    // bf16(scale * 2^118): exponent field e5 + 230 = (0x7300 >> 7) + e5
+    return x * 16u + nz * 0x73u;
 }
 
-// Dequantise one 16-byte chunk (32 weights of one row, k order, low nibble = even
-// k) into 16 packed 16-bit pairs.
-//   NVFP4 -> fp16:   w = f16(e2m1) * f16(scale)                    (exact)
-//   NVFP4 -> bf16:   w = bf16(e2m1 * 2^-112) * bf16(scale * 2^112)  (exact)
-//   MXFP4 -> bf16:   w * 4 (the 1/4 is folded into the epilogue scale)
+// Dequantise one 16-byte chunk (4 packed words = 32 weights of one row) into 16
+// registers of 16-bit pairs in k order (low half = even k).
 template <int MODE>
 __device__ __forceinline__ void dequant_chunk(const uint4 q, uint32_t mult, bool two_step,
-                                              const Consts &c, uint32_t (&out)[16]) {
+                                              uint32_t (&out)[16]) {
     const uint32_t words[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-        uint32_t h[4];
-        cvt_e2m1x8_to_f16x2x4(words[w], h[0], h[1], h[2], h[3]);
+        uint32_t x[4];
+        if (MODE == kModeNvF16)
+            extract_f16(words[w], x);
+        else
+            extract_bf16(words[w], x);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (MODE == kModeNvF16) {
-                out[w * 4 + j] = w < 2 ? hmul2_bcast<false, false>(h[j], mult)
-                                       : hmul2_bcast<false, true>(h[j], mult);
+                out[w * 4 + j] = w < 2 ? hmul2_bcast<false, false>(x[j], mult)
+                                       : hmul2_bcast<false, true>(x[j], mult);
             } else if (MODE == kModeNvBf16) {
-                const uint32_t t = f16x2_to_bf16x2_scaled(h[j], c);
-                out[w * 4 + j] = w < 2 ? hmul2_bcast<true, false>(t, mult)
-                                       : hmul2_bcast<true, true>(t, mult);
+                out[w * 4 + j] = w < 2 ? hmul2_bcast<true, false>(x[j], mult)
+                                       : hmul2_bcast<true, true>(x[j], mult);
             } else {
-                uint32_t t = f16x2_to_bf16x2_scaled(h[j], c);
-                if (two_step) t = hmul2_bf16(t, 0x77807780u); // * 2^112
+                uint32_t t = x[j];
+                if (two_step) t = hmul2_bf16(t, 0x7e807e80u); // * 2^126 (exact)
                 out[w * 4 + j] = hmul2_bf16(t, mult);
             }
         }
     }
-}
-
-// Power of two folded out of the A operand and applied in the epilogue.
-template <int MODE> __host__ __device__ constexpr float epilogue_factor() {
-    return MODE == kModeMxBf16 ? 0.25f : 1.0f; // 2^-2
 }
 
 } // namespace petit::dq

@@ -273,7 +273,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                                   &bars->full[s], pol_stream);
                     // token tile: box {64 k, NTOK tokens, kSubs slabs}
                     tma_load_3d(st, &tmap_act, &bars->full[s], 0, g.m_tile * NTOK, k_slab);
-                    if (it == 0) trace_stamp(args, 2);
                 }
                 __syncwarp();
                 w_src += w_stage_bytes;
@@ -338,9 +337,17 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
         const uint32_t c0 = kslice * kMyChunks;            // first chunk of this thread
         const uint32_t w_base = smem_u32(stage_base) + C::kActBytes;
         const uint32_t tmem_dst = tmem_a0 + ((quarter * 32) << 16) + c0 * 16;
-        const Consts dc = {args.two29, args.add64};
         uint32_t s = 0, ph = 0, ta = 0, ta_ph = 1; // ta_ph: parity to wait on a_empty
-        bool first = true;
+        // The four k-slice warps of a lane quarter share one SM sub-partition and run
+        // identical code; in lockstep they all hit the ALU-heavy (F2FP/LOP3) and the
+        // FMA-heavy (IMAD.HI/HMUL2) parts of the loop body together and each pipe
+        // idles half the time.  A one-off skew keeps them in different phases.
+        if (args.skew_cycles) {
+            const long long t0 = clock64();
+            const long long wait = (long long)kslice * args.skew_cycles;
+            while (clock64() - t0 < wait) {
+            }
+        }
         for (uint32_t u = u_begin; u < u_end;) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t rows = tile_rows(args.n, g.n_tile);
@@ -354,8 +361,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             for (uint32_t i = 0; i < n_stage; ++i) {
                 const uint32_t st = w_base + s * C::kStageBytes;
                 mbar_wait(&bars->full[s], ph);
-                if (first && threadIdx.x == kFirstDequantWarp * 32) trace_stamp(args, 3);
-                first = false;
                 uint4 q[kMyChunks];
 #pragma unroll
                 for (int ci = 0; ci < kMyChunks; ++ci) q[ci] = lds_v4(st + w_off + ci * rows * 16);
@@ -373,7 +378,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                     if (C::kIsMx) two_step = __any_sync(0xffffffffu, mx_needs_two_step(bits));
                     const uint32_t mult = chunk_multiplier<MODE>(bits, two_step);
                     uint32_t out[16];
-                    dequant_chunk<MODE>(q[ci], mult, two_step, dc, out);
+                    dequant_chunk<MODE>(q[ci], mult, two_step, out);
                     tmem_st_x16(tmem_dst + ta * C::kACols + ci * 16, out);
                 }
                 tmem_wait_st();

@@ -7,9 +7,14 @@
 // (32 consecutive k) per shared-memory load, and the whole (128 rows x 256 k)
 // block must be one contiguous range so a single cp.async.bulk fetches it.
 //
-// Weights  (u8, 2 nibbles per byte, low nibble = even k, order untouched so
-//           cvt.rn.f16x2.e2m1x2 can consume bytes directly):
-//   [n_tile = n/128][k_tile = k/256][chunk = (k%256)/32][row = n%128][16 bytes]
+// Weights: [n_tile = n/128][k_tile = k/256][chunk = (k%256)/32][row = n%128][16 bytes]
+//   Each 16-byte chunk is four 32-bit words of 8 consecutive k.  Inside a word the
+//   bits of the 8 e2m1 codes are permuted (pack_word) so that the pair (k=2p, 2p+1)
+//   comes out as a bf16x2 register -- sign at bit 15/31, exponent/mantissa bits at
+//   [8:6]/[24:22], i.e. the value times 2^-126 -- with ONE shift or rotate and ONE
+//   LOP3 (see dequant.cuh).  Measured on B200 the alternative (cvt.rn.f16x2.e2m1x2
+//   on native nibbles + fp16->bf16 re-bias) needs an IMAD.HI per pair that costs
+//   ~4.7 issue cycles on the FMA-heavy pipe and caps bf16 decode at ~47 % of HBM.
 //   A tile that is cut by N (rows R < 128, R % 16 == 0) keeps the same order
 //   with R rows, so the buffer is exactly N*K/2 bytes.
 // NVFP4 scales (one byte per 16 k, re-encoded E5M3):
@@ -22,7 +27,7 @@
 
 namespace petit::layout {
 
-constexpr int kLayoutVersion = 1;
+constexpr int kLayoutVersion = 2;
 constexpr uint32_t kTileN = 128;   // weight rows per tile (tcgen05 M)
 constexpr uint32_t kTileK = 256;   // k elements per scheduling unit
 constexpr uint32_t kChunkK = 32;   // k elements per 16-byte chunk
@@ -60,6 +65,48 @@ __host__ __device__ inline size_t scale_byte_offset(uint32_t n, uint32_t g,
     return (size_t)nt * kTileN * groups_per_row +
            (size_t)kt * rows * groups_per_tile_k +
            (size_t)ksub * rows * bytes_per_sub + (size_t)r * bytes_per_sub + j;
+}
+
+// Bit position (0..31) of {sign, e1, e0, m} of element i (0..7) inside a packed
+// word.  Pair p = i / 2, half h = i % 2 (0: low 16 bits).  The magnitude bits of
+// pairs 2 and 3 live in the OTHER half-word so that a 32-bit rotate brings both
+// elements of the pair home at once.
+struct NibbleBits {
+    uint8_t s, e1, e0, m;
+};
+__host__ __device__ inline NibbleBits packed_bits(uint32_t i) {
+    const uint32_t p = i >> 1, own = (i & 1) * 16, other = 16 - own;
+    switch (p) {
+    case 0: return {(uint8_t)(15 + own), (uint8_t)(8 + own), (uint8_t)(7 + own), (uint8_t)(6 + own)};
+    case 1: return {(uint8_t)(11 + own), (uint8_t)(4 + own), (uint8_t)(3 + own), (uint8_t)(2 + own)};
+    case 2: return {(uint8_t)(5 + own), (uint8_t)(14 + other), (uint8_t)(13 + other), (uint8_t)(12 + other)};
+    default: return {(uint8_t)(1 + own), (uint8_t)(10 + other), (uint8_t)(9 + other), (uint8_t)(0 + own)};
+    }
+}
+// native word (nibble i = element i = [s e1 e0 m] at bits 4i+3..4i) -> packed word
+__host__ __device__ inline uint32_t pack_word(uint32_t w) {
+    uint32_t o = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+        const NibbleBits b = packed_bits(i);
+        const uint32_t nib = (w >> (4 * i)) & 0xf;
+        o |= ((nib >> 3) & 1u) << b.s;
+        o |= ((nib >> 2) & 1u) << b.e1;
+        o |= ((nib >> 1) & 1u) << b.e0;
+        o |= (nib & 1u) << b.m;
+    }
+    return o;
+}
+__host__ __device__ inline uint32_t unpack_word(uint32_t o) {
+    uint32_t w = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) {
+        const NibbleBits b = packed_bits(i);
+        const uint32_t nib = (((o >> b.s) & 1u) << 3) | (((o >> b.e1) & 1u) << 2) |
+                             (((o >> b.e0) & 1u) << 1) | ((o >> b.m) & 1u);
+        w |= nib << (4 * i);
+    }
+    return w;
 }
 
 // e4m3 (positive, finite) -> unsigned E5M3: scale = 2^(e5-15) * (1 + m/8).

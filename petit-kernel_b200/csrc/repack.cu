@@ -6,8 +6,9 @@
 // launchers DequantNvFp4 / DequantMxFp4 / DequantPetitFp4 / DequantPetitMxFp4
 // (:614-727).  The target layout is the Blackwell tile layout of layout.cuh, so
 // the repack is a 16-byte block transpose (weights) and a 2/4-byte block
-// transpose plus an exact e4m3 -> E5M3 re-encode (NVFP4 scales); there is no
-// nibble permutation because cvt.rn.f16x2.e2m1x2 consumes native byte order.
+// transpose plus an exact e4m3 -> E5M3 re-encode (NVFP4 scales); inside each
+// 32-bit word the 8 nibbles are bit-permuted into the bf16-native order of
+// layout.cuh::pack_word (the role the reference's PetitFormat plays for MFMA).
 //
 // All kernels are pure data movement over N*K/2 bytes; they run once per layer
 // at weight-load time.  Each thread moves one 16-byte chunk; reads of a warp
@@ -40,10 +41,15 @@ repack_weights_kernel(uint4 *__restrict__ out, const uint4 *__restrict__ in, uin
         const uint32_t ck = (uint32_t)(i % chunks_per_row);
         const size_t native = (size_t)n * chunks_per_row + ck;
         const size_t packed = weight_byte_offset(n, ck * kChunkK, size_n, size_k) / 16;
-        if (kUnpack)
-            out[native] = in[packed];
-        else
-            out[packed] = in[native];
+        if (kUnpack) {
+            uint4 v = in[packed];
+            out[native] = make_uint4(unpack_word(v.x), unpack_word(v.y), unpack_word(v.z),
+                                     unpack_word(v.w));
+        } else {
+            uint4 v = in[native];
+            out[packed] = make_uint4(pack_word(v.x), pack_word(v.y), pack_word(v.z),
+                                     pack_word(v.w));
+        }
     }
 }
 
@@ -83,7 +89,7 @@ template <int MODE, bool kPacked>
 __global__ void __launch_bounds__(kThreads)
 dequant_dense_kernel(uint32_t *__restrict__ out, const uint8_t *__restrict__ w,
                      const uint8_t *__restrict__ sc, float global_scale, uint32_t size_n,
-                     uint32_t size_k, uint32_t two29, unsigned long long add64) {
+                     uint32_t size_k) {
     constexpr bool kIsMx = MODE == gemm::kModeMxBf16;
     constexpr bool kIsBf16 = MODE != gemm::kModeNvF16;
     constexpr uint32_t kGroup = kIsMx ? 32 : 16;
@@ -96,7 +102,7 @@ dequant_dense_kernel(uint32_t *__restrict__ out, const uint8_t *__restrict__ w,
         __nv_bfloat162 g = __float2bfloat162_rn(global_scale * dq::epilogue_factor<MODE>());
         gs2 = *reinterpret_cast<uint32_t *>(&g);
     } else {
-        __half2 g = __float2half2_rn(global_scale);
+        __half2 g = __float2half2_rn(global_scale * dq::epilogue_factor<MODE>());
         gs2 = *reinterpret_cast<uint32_t *>(&g);
     }
 
@@ -114,6 +120,7 @@ dequant_dense_kernel(uint32_t *__restrict__ out, const uint8_t *__restrict__ w,
             s1 = kIsMx ? s0 : sc[so + 1];
         } else {
             q = *reinterpret_cast<const uint4 *>(w + (size_t)n * (size_k / 2) + k0 / 2);
+            q = make_uint4(pack_word(q.x), pack_word(q.y), pack_word(q.z), pack_word(q.w));
             const size_t so = (size_t)n * (size_k / kGroup) + k0 / kGroup;
             s0 = kIsMx ? sc[so] : e4m3_to_e5m3(sc[so]);
             s1 = kIsMx ? s0 : e4m3_to_e5m3(sc[so + 1]);
@@ -121,9 +128,8 @@ dequant_dense_kernel(uint32_t *__restrict__ out, const uint8_t *__restrict__ w,
         const uint32_t bits = kIsMx ? s0 : (s0 | (s1 << 8));
         const bool two_step = kIsMx && dq::mx_needs_two_step(bits);
         const uint32_t mult = dq::chunk_multiplier<MODE>(bits, two_step);
-        const dq::Consts dc = {two29, add64};
         uint32_t v[16];
-        dq::dequant_chunk<MODE>(q, mult, two_step, dc, v);
+        dq::dequant_chunk<MODE>(q, mult, two_step, v);
         uint32_t *dst = out + ((size_t)n * size_k + k0) / 2;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -190,10 +196,10 @@ int dequant_dense(void *out, const void *w, const void *sc, float global_scale, 
 #define PETIT_DQ(MODE)                                                                        \
     if (packed)                                                                               \
         dequant_dense_kernel<MODE, true>                                                      \
-            <<<g, kThreads, 0, stream>>>(o, wp, sp, global_scale, size_n, size_k, 1u << 29, 0x70007000ull << 32); \
+            <<<g, kThreads, 0, stream>>>(o, wp, sp, global_scale, size_n, size_k); \
     else                                                                                      \
         dequant_dense_kernel<MODE, false>                                                     \
-            <<<g, kThreads, 0, stream>>>(o, wp, sp, global_scale, size_n, size_k, 1u << 29, 0x70007000ull << 32);
+            <<<g, kThreads, 0, stream>>>(o, wp, sp, global_scale, size_n, size_k);
     switch (mode) {
     case gemm::kModeNvF16: PETIT_DQ(gemm::kModeNvF16) break;
     case gemm::kModeNvBf16: PETIT_DQ(gemm::kModeNvBf16) break;

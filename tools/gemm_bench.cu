@@ -89,6 +89,43 @@ int main(int argc, char **argv) {
             float ms_total;
             cudaEventElapsedTime(&ms_total, e0, e1);
             double us = ms_total * 1e3 / r;
+            double us_graph = 0;
+            if (getenv("PETIT_GRAPH")) {
+                cudaStream_t st;
+                CK(cudaStreamCreate(&st));
+                // warm the per-stream workspace outside capture
+                int t2 = bf16 ? PETIT_DTYPE_BF16 : PETIT_DTYPE_FP16;
+                PetitSolutionHints h2 = {t2, mx ? PETIT_DTYPE_MXFP4_E2M1 : PETIT_DTYPE_FP4_E2M1, t2, 0};
+                auto call_s = [&](int i) {
+                    const uint8_t *wp = w + (size_t)(i % copies) * wbytes;
+                    const uint8_t *sp = sc + (size_t)(i % copies) * sbytes;
+                    int rc = mx ? petit_gemm_mxfp4_a16(c, a, wp, sp, d_gs, m, s.n, s.k, &h2, PETIT_SOLUTION_AUTO, (petit_stream_t)st)
+                                : petit_gemm_nvfp4_a16(c, a, wp, sp, d_gs, m, s.n, s.k, &h2, PETIT_SOLUTION_AUTO, (petit_stream_t)st);
+                    if (rc) { printf("gemm rc=%d\n", rc); exit(1); }
+                };
+                call_s(0);
+                CK(cudaStreamSynchronize(st));
+                cudaGraph_t graph;
+                cudaGraphExec_t exec;
+                CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                for (int i = 0; i < r; ++i) call_s(i);
+                CK(cudaStreamEndCapture(st, &graph));
+                CK(cudaGraphInstantiate(&exec, graph, 0));
+                CK(cudaGraphLaunch(exec, st));
+                CK(cudaStreamSynchronize(st));
+                CK(cudaEventRecord(e0, st));
+                CK(cudaGraphLaunch(exec, st));
+                CK(cudaEventRecord(e1, st));
+                CK(cudaStreamSynchronize(st));
+                float msg;
+                cudaEventElapsedTime(&msg, e0, e1);
+                us_graph = msg * 1e3 / r;
+                printf("  [graph replay of %d launches: %.2f us/launch, %.0f GB/s]\n", r, us_graph,
+                       ((double)wbytes + sbytes + 2.0 * m * s.k + 2.0 * m * s.n + 4) / us_graph * 1e-3);
+                cudaGraphExecDestroy(exec);
+                cudaGraphDestroy(graph);
+                cudaStreamDestroy(st);
+            }
             if (getenv("PETIT_TRACE")) {
                 unsigned long long *d_tr;
                 CK(cudaMalloc(&d_tr, 160 * 16 * 8));

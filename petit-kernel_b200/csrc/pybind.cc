@@ -1,0 +1,360 @@
+// PyTorch extension module `petit_kernel.ops`.
+//
+// Mirrors the reference's binding layer lib/pybind/{pybind.cc,fp4.cc}: same
+// function names, argument order, checks and error messages
+// (fp4.cc:38-283), re-targeted at the C ABI of libpetit_b200.so and
+// ATen/cuda.  Additions over the reference: a CUDA device
+// guard, shape/device checks on B and s in mul_nvfp4_a16, the DataType enum, the
+// Python-level get_fp4_solutions signature, and the unpack / dense-dequant test
+// hooks.  There is no CPU path: every op requires CUDA tensors.
+#include "causalflow/petit/petit.h"
+
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <vector>
+
+namespace py = pybind11;
+
+namespace {
+
+constexpr int64_t kLayoutM = 128; // fp4.cc:17 (k divisibility checked at repack)
+constexpr int64_t kLayoutN = 16;  // fp4.cc:18
+constexpr int64_t kPackFactor = 8;
+constexpr int64_t kKTile = 256;   // k granularity of the packed layout
+
+petit_stream_t stream_of(const torch::Tensor &t) {
+    return reinterpret_cast<petit_stream_t>(
+        at::cuda::getCurrentCUDAStream(t.get_device()).stream());
+}
+
+void check_status(int err, int64_t m, int64_t n, int64_t k, int64_t solution_id) {
+    // fp4.cc:201-206
+    if (err == PETIT_ERROR_PROBLEM_SHAPE) {
+        AT_ERROR("Incompatible problem shape (m=", m, ", n=", n, ", k=", k, ")");
+    } else if (err == PETIT_ERROR_KERNEL_SHAPE) {
+        AT_ERROR("No kernel implementation for solution_id=", solution_id, ".");
+    } else if (err != PETIT_OK) {
+        AT_ERROR("petit CUDA failure (code ", err, "): ",
+                 cudaGetErrorString(cudaGetLastError()));
+    }
+}
+
+PetitDataType dtype_of(const torch::Tensor &A) {
+    if (A.dtype() != torch::kBFloat16 && A.dtype() != torch::kFloat16) {
+        AT_ERROR("A must be bfloat16 or float16.");
+    }
+    return A.dtype() == torch::kBFloat16 ? PETIT_DTYPE_BF16 : PETIT_DTYPE_FP16;
+}
+
+// ---- fp4.cc:38-78 ------------------------------------------------------------
+torch::Tensor RepackNvFp4(torch::Tensor &b_q_weight, int64_t size_n, int64_t size_k) {
+    TORCH_CHECK(size_k % kLayoutM == 0, "size_k = ", size_k,
+                " is not divisible by tile_k_size = ", kLayoutM);
+    TORCH_CHECK(size_n % kLayoutN == 0, "size_n = ", size_n,
+                " is not divisible by tile_n_size = ", kLayoutN);
+    TORCH_CHECK((size_k / kPackFactor) == b_q_weight.size(1),
+                "Shape mismatch: b_q_weight.size(1) = ", b_q_weight.size(1),
+                ", size_k = ", size_k, ", pack_factor = ", kPackFactor);
+    TORCH_CHECK(b_q_weight.size(0) == size_n, "b_q_weight.size(0) = ", b_q_weight.size(0),
+                " is not size_n = ", size_n);
+    TORCH_CHECK(b_q_weight.device().is_cuda(), "b_q_weight is not on GPU");
+    TORCH_CHECK(b_q_weight.is_contiguous(), "b_q_weight is not contiguous");
+    TORCH_CHECK(b_q_weight.dtype() == at::kInt, "b_q_weight type is not kInt");
+    // the reference's kernel grid needs k % 256 (quantization_utils.cu:733-735)
+    TORCH_CHECK(size_k % kKTile == 0, "size_k = ", size_k,
+                " is not divisible by tile_k_size = ", kKTile);
+
+    c10::cuda::CUDAGuard guard(b_q_weight.device());
+    auto options = torch::TensorOptions().dtype(b_q_weight.dtype()).device(b_q_weight.device());
+    torch::Tensor out =
+        torch::empty({size_n / kLayoutN, size_k * kLayoutN / kPackFactor}, options);
+    int err = petit_repack_fp4_weights(reinterpret_cast<uint32_t *>(out.data_ptr()),
+                                       reinterpret_cast<const uint32_t *>(b_q_weight.data_ptr()),
+                                       size_k, size_n, stream_of(b_q_weight));
+    check_status(err, 0, size_n, size_k, -1);
+    return out;
+}
+
+torch::Tensor UnpackFp4(torch::Tensor &packed, int64_t size_n, int64_t size_k) {
+    TORCH_CHECK(packed.device().is_cuda() && packed.is_contiguous() && packed.dtype() == at::kInt,
+                "packed weights must be a contiguous CUDA int32 tensor");
+    TORCH_CHECK(packed.numel() == size_n * size_k / kPackFactor, "packed size mismatch");
+    c10::cuda::CUDAGuard guard(packed.device());
+    torch::Tensor out = torch::empty({size_n, size_k / kPackFactor}, packed.options());
+    int err = petit_unpack_fp4_weights(reinterpret_cast<uint32_t *>(out.data_ptr()),
+                                       reinterpret_cast<const uint32_t *>(packed.data_ptr()),
+                                       size_k, size_n, stream_of(packed));
+    check_status(err, 0, size_n, size_k, -1);
+    return out;
+}
+
+// ---- fp4.cc:80-121 -----------------------------------------------------------
+torch::Tensor ProcessNvFp4Scales(torch::Tensor &scales, int64_t size_n, int64_t size_k) {
+    constexpr int64_t kGroupM = 2 * kLayoutM;
+    TORCH_CHECK(size_k % kGroupM == 0, "size_k = ", size_k,
+                " is not divisible by tile_k_size = ", kGroupM);
+    TORCH_CHECK(size_n % kLayoutN == 0, "size_n = ", size_n,
+                " is not divisible by tile_n_size = ", kLayoutN);
+    int64_t group_size = size_k / scales.size(1);
+    if (group_size != 16) {
+        AT_ERROR("Only groupsize = 16 is supported.");
+    }
+    TORCH_CHECK(scales.size(0) == size_n, "scales.size(0) = ", scales.size(0),
+                " is not size_n = ", size_n);
+    TORCH_CHECK(scales.device().is_cuda(), "scales is not on GPU");
+    TORCH_CHECK(scales.is_contiguous(), "scales is not contiguous");
+    TORCH_CHECK(scales.dtype() == at::kFloat8_e4m3fn, "scales type is not float8_e4m3fn");
+
+    c10::cuda::CUDAGuard guard(scales.device());
+    auto options = torch::TensorOptions().dtype(scales.dtype()).device(scales.device());
+    torch::Tensor out = torch::empty({scales.size(0), scales.size(1)}, options);
+    int err = petit_repack_nvfp4_scales(out.data_ptr(), scales.data_ptr(), size_k, size_n,
+                                        stream_of(scales));
+    check_status(err, 0, size_n, size_k, -1);
+    return out;
+}
+
+// ---- fp4.cc:123-161 ----------------------------------------------------------
+torch::Tensor ProcessMxFp4Scales(torch::Tensor &scales, int64_t size_n, int64_t size_k) {
+    constexpr int64_t kScaleLayoutN = 32, kMxRowGroupSize = 32;
+    constexpr int64_t kGroupM = 2 * kLayoutM;
+    TORCH_CHECK(size_k % kGroupM == 0, "size_k = ", size_k,
+                " is not divisible by tile_k_size = ", kGroupM);
+    TORCH_CHECK(size_n % kLayoutN == 0, "size_n = ", size_n,
+                " is not divisible by tile_n_size = ", kLayoutN);
+    int64_t group_size = size_k / scales.size(1);
+    if (group_size != 32) {
+        AT_ERROR("Only groupsize = 32 is supported.");
+    }
+    TORCH_CHECK(scales.size(0) == size_n, "scales.size(0) = ", scales.size(0),
+                " is not size_n = ", size_n);
+    TORCH_CHECK(scales.device().is_cuda(), "scales is not on GPU");
+    TORCH_CHECK(scales.is_contiguous(), "scales is not contiguous");
+    TORCH_CHECK(scales.dtype() == at::kByte, "scales type is not uint8");
+    // the reference output shape [N/32, K] needs N % 32 (fp4.cc:146-148)
+    TORCH_CHECK(size_n % kScaleLayoutN == 0, "size_n = ", size_n,
+                " is not divisible by scale tile_n_size = ", kScaleLayoutN);
+
+    c10::cuda::CUDAGuard guard(scales.device());
+    auto options = torch::TensorOptions().dtype(scales.dtype()).device(scales.device());
+    torch::Tensor out = torch::empty(
+        {size_n / kScaleLayoutN, size_k * kScaleLayoutN / kMxRowGroupSize}, options);
+    int err = petit_repack_mxfp4_scales(out.data_ptr(), scales.data_ptr(), size_k, size_n,
+                                        stream_of(scales));
+    check_status(err, 0, size_n, size_k, -1);
+    return out;
+}
+
+void check_gemm_operands(const torch::Tensor &A, const torch::Tensor &B, const torch::Tensor &s,
+                         const torch::Tensor &global_scale, int64_t size_m, int64_t size_n,
+                         int64_t size_k, int64_t scale_bytes) {
+    TORCH_CHECK(A.device().is_cuda(), "A is not on GPU");
+    TORCH_CHECK(B.device() == A.device() && s.device() == A.device() &&
+                    global_scale.device() == A.device(),
+                "A, B, s and global_scale must be on the same CUDA device");
+    TORCH_CHECK(A.is_contiguous(), "A is not contiguous");
+    TORCH_CHECK(B.is_contiguous(), "B is not contiguous");
+    TORCH_CHECK(s.is_contiguous(), "s is not contiguous");
+    TORCH_CHECK(A.dim() == 2 && A.size(0) == size_m && A.size(1) == size_k,
+                "A must have shape [size_m, size_k]");
+    TORCH_CHECK(B.numel() * B.element_size() == size_n * size_k / 2,
+                "B does not hold size_n * size_k packed fp4 values");
+    TORCH_CHECK(s.numel() * s.element_size() == scale_bytes,
+                "s does not hold the processed scales of a [size_n, size_k] weight");
+    TORCH_CHECK(global_scale.dtype() == torch::kFloat32 && global_scale.numel() >= 1,
+                "global_scale must be a float32 tensor");
+}
+
+// ---- fp4.cc:163-209 ----------------------------------------------------------
+torch::Tensor MulNvFp4A16(const torch::Tensor &A, const torch::Tensor &B, const torch::Tensor &s,
+                          const torch::Tensor &global_scale, int64_t size_m, int64_t size_n,
+                          int64_t size_k, int64_t solution_id) {
+    int64_t groupsize = s.size(1) ? size_k / s.size(1) : 0;
+    if (groupsize != 16) {
+        AT_ERROR("Only groupsize = 16 is supported. size_k = ", size_k,
+                 ", s.size(1) = ", s.size(1));
+    }
+    PetitDataType a_type = dtype_of(A);
+    check_gemm_operands(A, B, s, global_scale, size_m, size_n, size_k, size_n * size_k / 16);
+
+    c10::cuda::CUDAGuard guard(A.device());
+    auto options = torch::TensorOptions().dtype(A.dtype()).device(A.device());
+    torch::Tensor c = torch::empty({size_m, size_n}, options);
+
+    PetitSolutionHints hints;
+    hints.a_type = a_type;
+    hints.b_type = PETIT_DTYPE_FP4_E2M1;
+    hints.c_type = a_type;
+    hints.require_high_precision = 0; // gfx90a workaround (fp4.cc:24-34): n/a on B200
+
+    int err = petit_gemm_nvfp4_a16(c.data_ptr(), A.data_ptr(), B.data_ptr(), s.data_ptr(),
+                                   global_scale.data_ptr<float>(), size_m, size_n, size_k, &hints,
+                                   static_cast<uint64_t>(solution_id), stream_of(A));
+    check_status(err, size_m, size_n, size_k, solution_id);
+    return c;
+}
+
+// ---- fp4.cc:211-260 ----------------------------------------------------------
+torch::Tensor MulMxFp4A16(const torch::Tensor &A, const torch::Tensor &B, const torch::Tensor &s,
+                          const torch::Tensor &global_scale, int64_t size_m, int64_t size_n,
+                          int64_t size_k, int64_t solution_id) {
+    TORCH_CHECK(B.size(0) == size_n / kLayoutN, "B.size(0) = ", B.size(0),
+                " is not size_n / 16 = ", size_n / kLayoutN);
+    TORCH_CHECK(B.size(1) == size_k * kLayoutN / kPackFactor, "B.size(1) = ", B.size(1),
+                " is not packed size = ", size_k * kLayoutN / kPackFactor);
+    TORCH_CHECK(s.size(0) == size_n / 32, "s.size(0) = ", s.size(0),
+                " is not size_n / 32 = ", size_n / 32);
+    TORCH_CHECK(s.size(1) == size_k, "s.size(1) = ", s.size(1), " is not size_k = ", size_k);
+    PetitDataType a_type = dtype_of(A);
+    check_gemm_operands(A, B, s, global_scale, size_m, size_n, size_k, size_n * size_k / 32);
+
+    c10::cuda::CUDAGuard guard(A.device());
+    auto options = torch::TensorOptions().dtype(A.dtype()).device(A.device());
+    torch::Tensor c = torch::empty({size_m, size_n}, options);
+
+    PetitSolutionHints hints;
+    hints.a_type = a_type;
+    hints.b_type = PETIT_DTYPE_MXFP4_E2M1;
+    hints.c_type = a_type;
+    hints.require_high_precision = 0;
+
+    int err = petit_gemm_mxfp4_a16(c.data_ptr(), A.data_ptr(), B.data_ptr(), s.data_ptr(),
+                                   global_scale.data_ptr<float>(), size_m, size_n, size_k, &hints,
+                                   static_cast<uint64_t>(solution_id), stream_of(A));
+    check_status(err, size_m, size_n, size_k, solution_id);
+    return c;
+}
+
+// ---- fp4.cc:262-283 ----------------------------------------------------------
+py::list GetNvFp4Solutions(const PetitSolutionHints &hints, int64_t size_m, int64_t size_n,
+                           int64_t size_k) {
+    unsigned n_solutions = 0;
+    int err = petit_get_solutions(&hints, size_m, size_n, size_k, nullptr, &n_solutions);
+    if (err != 0) {
+        AT_ERROR("Failed to get solutions: ", err);
+    }
+    std::vector<uint64_t> solutions(n_solutions);
+    err = petit_get_solutions(&hints, size_m, size_n, size_k, solutions.data(), &n_solutions);
+    if (err != 0) {
+        AT_ERROR("Failed to get solutions: ", err);
+    }
+    py::list ret;
+    for (unsigned i = 0; i < n_solutions; ++i) ret.append(solutions[i]);
+    return ret;
+}
+
+int dtype_code(py::object dt) {
+    auto t = torch::python::detail::py_object_to_dtype(dt);
+    if (t == torch::kBFloat16) return PETIT_DTYPE_BF16;
+    if (t == torch::kFloat16) return PETIT_DTYPE_FP16;
+    AT_ERROR("a_type / c_type must be torch.bfloat16 or torch.float16");
+}
+
+// Accepts both the reference's bound form (hints, m, n, k) (pybind.cc:14-17) and the
+// form its Python wrapper actually passes (m, n, k, a_type, c_type)
+// (petit_kernel/__init__.py:63-66); the latter raises TypeError in the reference.
+py::list GetFp4Solutions(py::args args, py::kwargs kwargs) {
+    if (args.size() >= 1 && py::isinstance<PetitSolutionHints>(args[0])) {
+        TORCH_CHECK(args.size() == 4, "get_fp4_solutions(hints, size_m, size_n, size_k)");
+        return GetNvFp4Solutions(args[0].cast<PetitSolutionHints>(), args[1].cast<int64_t>(),
+                                 args[2].cast<int64_t>(), args[3].cast<int64_t>());
+    }
+    TORCH_CHECK(args.size() == 5,
+                "get_fp4_solutions(size_m, size_n, size_k, a_type, c_type[, b_type=])");
+    PetitSolutionHints hints;
+    hints.a_type = dtype_code(args[3]);
+    hints.c_type = dtype_code(args[4]);
+    hints.b_type = PETIT_DTYPE_FP4_E2M1;
+    if (kwargs.contains("b_type")) hints.b_type = kwargs["b_type"].cast<int>();
+    hints.require_high_precision = 0;
+    return GetNvFp4Solutions(hints, args[0].cast<int64_t>(), args[1].cast<int64_t>(),
+                             args[2].cast<int64_t>());
+}
+
+// Dense dequant hooks (fp4/gemm_fp4.h:11-21, quantization_utils.cu:614-727).
+torch::Tensor DequantDense(const torch::Tensor &w, const torch::Tensor &scales, double global_scale,
+                           py::object out_dtype, int64_t size_n, int64_t size_k, bool mx,
+                           bool packed) {
+    TORCH_CHECK(w.device().is_cuda() && scales.device().is_cuda(), "tensors must be on GPU");
+    TORCH_CHECK(w.is_contiguous() && scales.is_contiguous(), "tensors must be contiguous");
+    c10::cuda::CUDAGuard guard(w.device());
+    auto dt = torch::python::detail::py_object_to_dtype(out_dtype);
+    int code = dt == torch::kBFloat16 ? PETIT_DTYPE_BF16
+                                      : (dt == torch::kFloat16 ? PETIT_DTYPE_FP16 : -1);
+    torch::Tensor out =
+        torch::empty({size_n, size_k}, torch::TensorOptions().dtype(dt).device(w.device()));
+    int err;
+    auto st = stream_of(w);
+    if (mx)
+        err = packed ? petit_dequant_packed_mxfp4(out.data_ptr(), w.data_ptr(), scales.data_ptr(),
+                                                  global_scale, code, size_k, size_n, st)
+                     : petit_dequant_mxfp4(out.data_ptr(), w.data_ptr(), scales.data_ptr(),
+                                           global_scale, code, size_k, size_n, st);
+    else
+        err = packed ? petit_dequant_packed_nvfp4(out.data_ptr(), w.data_ptr(), scales.data_ptr(),
+                                                  global_scale, code, size_k, size_n, st)
+                     : petit_dequant_nvfp4(out.data_ptr(), w.data_ptr(), scales.data_ptr(),
+                                           global_scale, code, size_k, size_n, st);
+    TORCH_CHECK(err == 0, "dequant hook failed with code ", err,
+                " (bad shape or unsupported output type)");
+    return out;
+}
+
+} // namespace
+
+PYBIND11_MODULE(ops, m) {
+    // pybind.cc:9-25 of the reference
+    m.def("repack_nvfp4", &RepackNvFp4, "Repack NVFP4 to Petit FP4", py::arg("qw"),
+          py::arg("size_n"), py::arg("size_k"));
+    m.def("process_nvfp4_scales", &ProcessNvFp4Scales, "Process NVFP4 scales", py::arg("scales"),
+          py::arg("size_n"), py::arg("size_k"));
+    m.def("process_mxfp4_scales", &ProcessMxFp4Scales, "Process MXFP4 scales", py::arg("scales"),
+          py::arg("size_n"), py::arg("size_k"));
+    m.def("mul_nvfp4_a16", &MulNvFp4A16, "Multiply NVFP4 FP16", py::arg("a"), py::arg("b"),
+          py::arg("s"), py::arg("global_scale"), py::arg("size_m"), py::arg("size_n"),
+          py::arg("size_k"), py::arg("solution_id") = -1);
+    m.def("mul_mxfp4_a16", &MulMxFp4A16, "Multiply MXFP4 FP16", py::arg("a"), py::arg("b"),
+          py::arg("s"), py::arg("global_scale"), py::arg("size_m"), py::arg("size_n"),
+          py::arg("size_k"), py::arg("solution_id") = -1);
+    m.def("get_nvfp4_solutions", &GetNvFp4Solutions, "Get possible fp4 solutions");
+    m.def("get_fp4_solutions", &GetFp4Solutions, "Get possible fp4 solutions");
+
+    py::class_<PetitSolutionHints>(m, "PetitSolutionHints")
+        .def(py::init([]() {
+            PetitSolutionHints h;
+            h.a_type = PETIT_DTYPE_BF16;
+            h.b_type = PETIT_DTYPE_FP4_E2M1;
+            h.c_type = PETIT_DTYPE_BF16;
+            h.require_high_precision = 0;
+            return h;
+        }))
+        .def_readwrite("a_type", &PetitSolutionHints::a_type)
+        .def_readwrite("b_type", &PetitSolutionHints::b_type)
+        .def_readwrite("c_type", &PetitSolutionHints::c_type)
+        .def_property(
+            "require_high_precision",
+            [](const PetitSolutionHints &h) { return h.require_high_precision != 0; },
+            [](PetitSolutionHints &h, bool v) { h.require_high_precision = v ? 1 : 0; });
+
+    // the C++ DataType values (types.h:4-13), not registered in the reference
+    py::enum_<PetitDataType>(m, "CDataType")
+        .value("kDataTypeInt4", PETIT_DTYPE_INT4)
+        .value("kDataTypeFp8e4m3", PETIT_DTYPE_FP8_E4M3)
+        .value("kDataTypeFp8e8m0", PETIT_DTYPE_FP8_E8M0)
+        .value("kDataTypeFp4e2m1", PETIT_DTYPE_FP4_E2M1)
+        .value("kDataTypeFp16", PETIT_DTYPE_FP16)
+        .value("kDataTypeBf16", PETIT_DTYPE_BF16)
+        .value("kDataTypeFp8e5m2Fnuz", PETIT_DTYPE_FP8_E5M2_FNUZ)
+        .value("kDataTypeMxFp4e2m1", PETIT_DTYPE_MXFP4_E2M1)
+        .export_values();
+
+    // extras: round-trip / bit-exactness hooks and introspection
+    m.def("unpack_fp4", &UnpackFp4, "Inverse of repack_nvfp4 (test hook)");
+    m.def("dequant_dense", &DequantDense, "Dense dequantisation hook", py::arg("w"),
+          py::arg("scales"), py::arg("global_scale"), py::arg("out_dtype"), py::arg("size_n"),
+          py::arg("size_k"), py::arg("mx"), py::arg("packed"));
+    m.def("solution_name", [](uint64_t id) { return std::string(petit_solution_name(id)); });
+    m.def("packed_layout_version", []() { return petit_packed_layout_version(); });
+}

@@ -1,0 +1,98 @@
+"""Tensor-parallel sharding of the FP4 GEMM the way Llama-3.3-70B TP shards it.
+
+The reference has no distributed code: TP lives in its callers,
+which shard the checkpoint, repack the local shard and all-reduce row-parallel
+outputs.  Its benchmark list already contains the TP=8 shard shapes
+(tools/benchmarks/matmul.py:18-25).  This module is that caller-side logic:
+
+* column-parallel (qkv, gate_up): split N -> independent GEMMs, no collective;
+* row-parallel (o_proj, down_proj): split K (on scale-group boundaries) -> partial
+  [M, N] outputs summed by ONE all-reduce (NCCL over NVLink on GPUs).
+
+The slicing helpers are pure tensor indexing (usable on CPU, e.g. under gloo in the
+tests); the Linear classes call the CUDA ops of ``petit_kernel`` and nothing else.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+# Llama-3.3-70B decoder-layer GEMMs: name -> (N, K, parallel kind)
+LLAMA70B_LAYER = {
+    "qkv": (10240, 8192, "column"),
+    "o": (8192, 8192, "row"),
+    "gate_up": (57344, 8192, "column"),
+    "down": (8192, 28672, "row"),
+}
+
+
+def shard_shape(n: int, k: int, kind: str, tp: int) -> tuple[int, int]:
+    """Per-rank (N, K) of a layer; N splits stay multiples of 64, K splits of 256."""
+    if kind == "column":
+        assert n % (tp * 64) == 0, "N shard must be a multiple of 64"
+        return n // tp, k
+    assert k % (tp * 256) == 0, "K shard must be a multiple of 256"
+    return n, k // tp
+
+
+def column_shard(q_u8: torch.Tensor, scales: torch.Tensor, tp: int, rank: int):
+    """N-split: rows [rank*N/tp, (rank+1)*N/tp) of weights [N, K/2] and scales [N, K/g]."""
+    n = q_u8.shape[0]
+    lo, hi = rank * n // tp, (rank + 1) * n // tp
+    return q_u8[lo:hi].contiguous(), scales[lo:hi].contiguous()
+
+
+def row_shard(q_u8: torch.Tensor, scales: torch.Tensor, tp: int, rank: int):
+    """K-split: k in [rank*K/tp, (rank+1)*K/tp); the cut falls on scale-group
+    boundaries because K/tp is a multiple of 256."""
+    kb, kg = q_u8.shape[1], scales.shape[1]
+    return (q_u8[:, rank * kb // tp:(rank + 1) * kb // tp].contiguous(),
+            scales[:, rank * kg // tp:(rank + 1) * kg // tp].contiguous())
+
+
+def row_shard_activation(a: torch.Tensor, tp: int, rank: int) -> torch.Tensor:
+    k = a.shape[1]
+    return a[:, rank * k // tp:(rank + 1) * k // tp].contiguous()
+
+
+def all_reduce_sum(c: torch.Tensor, group=None) -> torch.Tensor:
+    """The one collective of the row-parallel layers."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
+    return c
+
+
+@dataclass
+class PackedLinear:
+    """One FP4 linear layer resident on the current CUDA device."""
+    b: torch.Tensor
+    s: torch.Tensor
+    global_scale: torch.Tensor
+    n: int
+    k: int
+    fmt: str          # "nvfp4" | "mxfp4"
+    kind: str         # "column" | "row"
+
+    @classmethod
+    def from_native(cls, q_u8, scales, global_scale, fmt: str, kind: str):
+        import petit_kernel as pk  # CUDA extension; no fallback
+
+        n, k = q_u8.shape[0], q_u8.shape[1] * 2
+        qw = q_u8.cuda().contiguous().view(torch.int32)
+        if fmt == "nvfp4":
+            b, s = pk.repack_nvfp4(qw, n, k), pk.process_nvfp4_scales(scales.cuda(), n, k)
+        else:
+            b, s = pk.repack_mxfp4(qw, n, k), pk.process_mxfp4_scales(scales.cuda(), n, k)
+        return cls(b, s, global_scale.cuda(), n, k, fmt, kind)
+
+    def forward(self, a: torch.Tensor, group=None, reduce: bool = True) -> torch.Tensor:
+        import petit_kernel as pk
+
+        m = a.shape[0]
+        mul = pk.mul_nvfp4_a16 if self.fmt == "nvfp4" else pk.mul_mxfp4_a16
+        c = mul(a, self.b, self.s, self.global_scale, m, self.n, self.k, -1)
+        if self.kind == "row" and reduce:
+            all_reduce_sum(c, group)
+        return c

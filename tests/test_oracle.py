@@ -1,0 +1,128 @@
+"""CPU tests: the oracle is pinned to the reference's own oracle (golden vectors made
+by running /root/reference code, tests/golden/make_golden.py) and is internally
+consistent (numpy vs plain-C restatement, exactness in 16 bits)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, oracle_c_lib, orc, from_bits16
+
+NVFP4_CASES = [(64, 128, 256, 1234), (96, 64, 512, 2026)]  # test_fp4_gemm_quark.py:27-30
+MXFP4_CASES = [(64, 128, 256, 1234), (96, 96, 512, 2026)]  # :32-35
+
+
+def test_e4m3_decode_matches_torch_all_256():
+    bits = np.arange(256, dtype=np.uint8)
+    ref = torch.from_numpy(bits.copy()).view(torch.float8_e4m3fn).float().numpy()
+    got = orc.e4m3_to_f32(bits)
+    assert np.array_equal(np.isnan(ref), np.isnan(got))
+    ok = ~np.isnan(ref)
+    assert np.array_equal(ref[ok].view(np.uint32), got[ok].view(np.uint32))
+
+
+def test_e8m0_decode_is_bf16_shift():
+    bits = np.arange(256, dtype=np.uint8)
+    got = orc.e8m0_to_f32(bits)
+    assert got[0] == 0.0 and np.isinf(got[255])          # reference's shift semantics
+    assert np.array_equal(got[1:255], np.ldexp(1.0, np.arange(1, 255) - 127).astype(np.float32))
+
+
+def test_nvfp4_exhaustive_table_matches_reference_oracle():
+    g = golden("nvfp4_exhaustive.npz")
+    sb = g["scale_bits"]
+    q = np.repeat((np.arange(16, dtype=np.uint8) * 0x11)[:, None], len(sb) * 8, axis=1)
+    w = orc.dequant_nvfp4(q, np.tile(sb, (16, 1))).reshape(16, len(sb), 16)
+    assert np.array_equal(w[:, :, 0].view(np.uint32), g["table"].view(np.uint32))
+    assert np.array_equal(w[:, :, 0], w[:, :, 15])
+    # ground truth of ExhaustiveFp4DequantTest: scale.to_fp32() * fp4_values[q]
+    expect = orc.E2M1_VALUES[:, None] * orc.e4m3_to_f32(sb)[None, :]
+    assert np.array_equal(expect.view(np.uint32), g["table"].view(np.uint32))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_dequantised_weights_are_exact_in_16_bits(dtype):
+    g = golden("nvfp4_exhaustive.npz")
+    t = torch.from_numpy(g["table"].copy())
+    assert torch.equal(t.to(dtype).float(), t)
+
+
+@pytest.mark.parametrize("m,n,k,seed", NVFP4_CASES)
+def test_nvfp4_gemm_ref_matches_reference_oracle(m, n, k, seed):
+    g = golden("nvfp4_gemm_cases.npz")
+    tag = f"m{m}_n{n}_k{k}_s{seed}"
+    a, q, s, gs = orc.make_nvfp4_case(m, n, k, seed)
+    w = orc.dequant_nvfp4(q.numpy(), s.view(torch.uint8).numpy())
+    assert np.array_equal(w[0].view(np.uint32), g[f"{tag}_w_row0"].view(np.uint32))
+    assert np.allclose([w.astype(np.float64).sum(), np.abs(w).astype(np.float64).sum()],
+                       g[f"{tag}_wsum"], rtol=0, atol=0)
+    c = orc.nvfp4_gemm_ref(a, q, s, gs)
+    c_gold = from_bits16(g[f"{tag}_c"], torch.bfloat16)
+    # same torch fp32 matmul on the same machine class: identical up to 1 bf16 ulp
+    torch.testing.assert_close(c.float(), c_gold.float(), rtol=8e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("m,n,k,seed", MXFP4_CASES)
+def test_mxfp4_vectors_are_stable(m, n, k, seed):
+    g = golden("mxfp4_cases.npz")
+    a, q, s, gs = orc.make_mxfp4_case(m, n, k, seed)
+    c = orc.mxfp4_gemm_ref(a, q, s, gs)
+    c_gold = from_bits16(g[f"m{m}_n{n}_k{k}_s{seed}_c"], torch.bfloat16)
+    torch.testing.assert_close(c.float(), c_gold.float(), rtol=8e-3, atol=0)
+
+
+def test_mxfp4_exhaustive_formula():
+    g = golden("mxfp4_cases.npz")["exhaustive_table"]
+    sb = np.arange(1, 238)
+    expect = orc.E2M1_VALUES[:, None] * np.ldexp(1.0, sb - 127)[None, :].astype(np.float32)
+    assert np.array_equal(expect.astype(np.float32).view(np.uint32), g.view(np.uint32))
+    t = torch.from_numpy(g.copy())
+    assert torch.equal(t.to(torch.bfloat16).float(), t)  # exact in bf16 on [1, 237]
+
+
+def test_c_oracle_matches_numpy_oracle():
+    lib = oracle_c_lib()
+    lib.petit_oracle_e4m3.restype = ctypes.c_float
+    lib.petit_oracle_e4m3.argtypes = [ctypes.c_uint8]
+    for b in range(256):
+        v = lib.petit_oracle_e4m3(b)
+        r = orc.e4m3_to_f32(np.array([b], dtype=np.uint8))[0]
+        assert (np.isnan(v) and np.isnan(r)) or v == r
+    n, k = 48, 512
+    rs = np.random.RandomState(0)
+    q = rs.randint(0, 256, size=(n, k // 2)).astype(np.uint8)
+    s_nv = rs.randint(1, 0x7F, size=(n, k // 16)).astype(np.uint8)
+    s_mx = rs.randint(1, 238, size=(n, k // 32)).astype(np.uint8)
+    out = np.empty((n, k), dtype=np.float32)
+    f32p = ctypes.POINTER(ctypes.c_float)
+    u8p = ctypes.POINTER(ctypes.c_uint8)
+    for fn, s, ref in ((lib.petit_oracle_dequant_nvfp4, s_nv, orc.dequant_nvfp4),
+                       (lib.petit_oracle_dequant_mxfp4, s_mx, orc.dequant_mxfp4)):
+        fn.argtypes = [f32p, u8p, u8p, ctypes.c_size_t, ctypes.c_size_t]
+        fn(out.ctypes.data_as(f32p), q.ctypes.data_as(u8p), s.ctypes.data_as(u8p), n, k)
+        assert np.array_equal(out.view(np.uint32), ref(q, s).view(np.uint32))
+    # 16-bit conversions (round to nearest even) against torch
+    lib.petit_oracle_f32_to_bf16.restype = ctypes.c_uint16
+    lib.petit_oracle_f32_to_bf16.argtypes = [ctypes.c_float]
+    lib.petit_oracle_f32_to_f16.restype = ctypes.c_uint16
+    lib.petit_oracle_f32_to_f16.argtypes = [ctypes.c_float]
+    vals = np.concatenate([rs.randn(2000).astype(np.float32) * 100,
+                           rs.randn(500).astype(np.float32) * 1e-6,
+                           np.array([0.0, -0.0, 65504.0, 65520.0, 1e-8, 6e-8], dtype=np.float32)])
+    tb = torch.from_numpy(vals).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    th = torch.from_numpy(vals).to(torch.float16).view(torch.int16).numpy().view(np.uint16)
+    for v, eb, eh in zip(vals, tb, th):
+        assert lib.petit_oracle_f32_to_bf16(float(v)) == eb
+        assert lib.petit_oracle_f32_to_f16(float(v)) == eh
+
+
+def test_matcher_and_pm0_helpers():
+    a = torch.tensor([1.0, 100.0, 0.0, -0.0])
+    b = torch.tensor([1.009, 100.9, -0.0, 0.0])
+    assert orc.is_near_cpp(a, b).all()
+    assert not orc.is_near_cpp(torch.tensor([1.02]), torch.tensor([1.0])).any()
+    x = torch.tensor([0.0, 1.5], dtype=torch.bfloat16)
+    y = torch.tensor([-0.0, 1.5], dtype=torch.bfloat16)
+    assert orc.bits_equal_pm0(x, y)
+    assert not orc.bits_equal_pm0(x, torch.tensor([0.0, 1.25], dtype=torch.bfloat16))

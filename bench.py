@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- FP4 x BF16 GEMM benchmark (BASELINE.json metric) for the B200 build.
+
+Workload (config.workload): the four NVFP4 GEMMs of one Llama-3.3-70B decoder layer
+(qkv 10240x8192, o 8192x8192, gate_up 57344x8192, down 8192x28672) at M = 16 decode
+tokens, bf16 activations -- BASELINE.json configs[1].  One "step" = one pass over the
+layer set.  With --gpus N > 1 the layer is tensor-parallel over N ranks exactly as
+Llama TP shards it (qkv/gate_up N-split, no collective; o/down K-split + one NCCL
+all-reduce each), so total work is fixed ("strong" scaling).
+
+value  = algorithmic bytes of the whole (unsharded) layer set per second, inputs
+         resident in HBM, CUDA-event timed, max over ranks.
+e2e    = same, through the public petit_kernel Python API with the activations coming
+         from pinned host memory and the outputs copied back, every step.
+roofline / cpu_baseline / clocks / details: see DESIGN.md "Measurement".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--m M]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "petit-kernel_b200"))
+sys.path.insert(0, ROOT)
+
+LAYER = [("qkv", 10240, 8192, "column"), ("o", 8192, 8192, "row"),
+         ("gate_up", 57344, 8192, "column"), ("down", 8192, 28672, "row")]
+METRIC = "FP4xBF16 GEMM algorithmic HBM GB/s, Llama-3.3-70B decoder-layer GEMM set (NVFP4, M=16)"
+
+
+def algo_bytes(m, n, k, group=16):
+    # fp4 + scales + A + C + global scale
+    return n * k // 2 + n * k // group + 2 * m * k + 2 * m * n + 4
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "20"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def wait_started(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        return len(self.samples)
+
+    def stop(self, lo=0, hi=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        window = self.samples[lo:hi] or self.samples
+        self.samples = window
+        mhz = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for nm, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        mx = next((int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()), None)
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(mhz)}
+
+
+# ------------------------------------------------------------------ CPU reference arm
+def cpu_reference_rate(m, shapes, reps):
+    """The reference's CPU path (torch dequantise + fp32 matmul,
+    tests/ops/test_fp4_gemm_quark.py:9-24) restated in oracle/, on the host cores."""
+    from oracle import petit_oracle as orc
+
+    g = torch.Generator().manual_seed(0)
+    total_bytes, total_s = 0, 0.0
+    for (_, n, k, _) in shapes:
+        a = torch.randn((m, k), generator=g).to(torch.bfloat16)
+        q = torch.randint(0, 256, (n, k // 2), generator=g, dtype=torch.uint8)
+        s = (torch.rand((n, k // 16), generator=g) * 3.5 + 0.25).to(torch.float8_e4m3fn)
+        gs = torch.ones(1)
+        orc.nvfp4_gemm_ref_torch(a[:, :256], q[:64, :128], s[:64, :16], gs)  # warm torch
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            orc.nvfp4_gemm_ref_torch(a, q, s, gs)
+        total_s += time.perf_counter() - t0
+        total_bytes += reps * algo_bytes(m, n, k)
+    return total_bytes / total_s / 1e9, total_s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shapes = [LAYER[1]]  # o_proj 8192 x 8192: bounded sample of the layer set
+    steps = max(1, min(args.steps, 5))
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_rate(args.m, shapes, 1)
+    t0 = time.perf_counter()
+    gbs, secs = cpu_reference_rate(args.m, shapes, steps)
+    wall = time.perf_counter() - t0
+    out = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": torch.get_num_threads(),
+                         "kind": "port",
+                         "sample": f"o_proj 8192x8192 NVFP4 M={args.m}, {steps} passes of torch "
+                                   f"dequant+fp32 matmul (oracle/petit_oracle.py), {wall:.1f} s"},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def workload_config(args, world):
+    return {"workload": f"Llama-3.3-70B decoder-layer GEMM set qkv/o/gate_up/down, NVFP4 weights, "
+                        f"bf16 activations, M={args.m}",
+            "m": args.m, "shapes": {n: [a, b] for n, a, b, _ in LAYER},
+            "parallelism": f"tp{world}" if world > 1 else "single",
+            "l2": "weights rotate over distinct copies > 2x L2 (126 MB) between reuses"}
+
+
+# ------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--m", type=int, default=16)
+    ap.add_argument("--no-details", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import petit_kernel as pk  # fails loudly without the CUDA extension
+    import petit_tp
+
+    dev = torch.device("cuda", local)
+    m = args.m
+    hbm_peak, tf_peak, peak_src = peaks()
+
+    # ---- build the (sharded) layer set, several distinct copies to defeat L2
+    shard = [(nm,) + petit_tp.shard_shape(n, k, kind, world) + (kind,) for nm, n, k, kind in LAYER]
+    set_bytes = sum(n * k // 2 + n * k // 16 for _, n, k, _ in shard)
+    copies = max(2, int(300e6 // set_bytes) + 2)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    layers = []
+    for _ in range(copies):
+        one = []
+        for nm, n, k, kind in shard:
+            q = torch.randint(0, 256, (n, k // 2), generator=g, dtype=torch.uint8, device=dev)
+            s = (torch.rand((n, k // 16), generator=g, device=dev) * 3.5 + 0.25).to(torch.float8_e4m3fn)
+            b = pk.repack_nvfp4(q.view(torch.int32), n, k)
+            sp = pk.process_nvfp4_scales(s, n, k)
+            one.append((nm, n, k, kind, b, sp))
+            del q, s
+        layers.append(one)
+    gs = torch.rand(1, generator=g, device=dev) * 1.5 + 0.5
+    acts = {k: torch.randn((m, k), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+            for k in {k for _, _, k, _ in shard}}
+
+    def layer_step(i, a_by_k=acts):
+        outs = []
+        for nm, n, k, kind, b, sp in layers[i % copies]:
+            c = pk.mul_nvfp4_a16(a_by_k[k], b, sp, gs, m, n, k, -1)
+            if kind == "row" and world > 1:
+                dist.all_reduce(c)
+            outs.append(c)
+        return outs
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    full_bytes = sum(algo_bytes(m, n, k) for _, n, k, _ in LAYER)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- device-resident timing
+    for i in range(args.warmup):
+        layer_step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_started()
+    sync()
+    lo = sampler.mark()
+    e0.record()
+    for i in range(args.steps):
+        layer_step(i)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    hi = sampler.mark()
+    if hi - lo < 3:
+        # timed region shorter than the 20 ms sampling period: keep the same load
+        # running (untimed) until a few samples exist
+        t_end = time.time() + 0.25
+        i = 0
+        while time.time() < t_end:
+            layer_step(i)
+            i += 1
+        torch.cuda.synchronize()
+        hi = sampler.mark()
+    clocks = sampler.stop(lo, hi) if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "timed region" if hi - lo >= 3 else "timed region + same load repeated"
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = full_bytes / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end: host activations in, host outputs out, every step
+    host_a = {k: v.cpu().pin_memory() for k, v in acts.items()}
+    dev_a = {k: torch.empty_like(v) for k, v in acts.items()}
+    host_c = [torch.empty((m, n), dtype=torch.bfloat16).pin_memory() for _, n, _, _ in shard]
+
+    def e2e_step(i):
+        for k in dev_a:
+            dev_a[k].copy_(host_a[k], non_blocking=True)
+        outs = layer_step(i, dev_a)
+        for h, c in zip(host_c, outs):
+            h.copy_(c, non_blocking=True)
+
+    for i in range(args.warmup):
+        e2e_step(i)
+    sync()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = full_bytes / (t.item() / args.steps * 1e-3) / 1e9
+    h2d = sum(v.numel() * 2 for v in host_a.values())
+    d2h = sum(h.numel() * 2 for h in host_c)
+
+    # ---- roofline of the dominant kernel (the stream-K GEMM), per launch, live
+    per_launch = []
+    for nm, n, k, kind, _, _ in layers[0]:
+        for i in range(3):
+            b, sp = layers[i % copies][[x[0] for x in layers[0]].index(nm)][4:6]
+            pk.mul_nvfp4_a16(acts[k], b, sp, gs, m, n, k, -1)
+        torch.cuda.synchronize()
+        reps = 20
+        e0.record()
+        for i in range(reps):
+            b, sp = layers[i % copies][[x[0] for x in layers[0]].index(nm)][4:6]
+            pk.mul_nvfp4_a16(acts[k], b, sp, gs, m, n, k, -1)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / reps * 1e3
+        per_launch.append({"gemm": nm, "n": n, "k": k, "us": round(us, 2),
+                           "gbs": round(algo_bytes(m, n, k) / us * 1e-3, 1),
+                           "frac_hbm": round(algo_bytes(m, n, k) / us * 1e-3 / hbm_peak, 4)})
+    shard_bytes = sum(algo_bytes(m, n, k) for _, n, k, _ in shard)
+    avg_launch_us = sum(p["us"] for p in per_launch) / len(per_launch)
+    achieved = (shard_bytes / len(shard)) / avg_launch_us * 1e-3
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")) as f:
+            traffic = json.load(f).get("avg_bytes_per_launch_m16")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
+                "peak_source": peak_src, "kernel": "fp4_gemm_kernel<nvfp4,bf16,tok16> (stream-K tcgen05)",
+                "per_launch": per_launch}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    details = None
+    if world == 1 and not args.no_details:
+        details = sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak)
+
+    cores = torch.get_num_threads()
+    t0 = time.perf_counter()
+    cpu_gbs, cpu_s = cpu_reference_rate(m, [LAYER[1]], 2)
+    cpu = {"value": round(cpu_gbs, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+           "sample": f"o_proj 8192x8192 NVFP4 M={m}, 2 passes of the torch dequant+fp32-matmul "
+                     f"oracle on the host ({time.perf_counter() - t0:.1f} s)"}
+
+    out = {
+        "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 5),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(args, world),
+        "e2e": {"value": round(e2e_value, 1), "unit": "GB/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": args.steps * len(shard),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "frac_of_hbm_peak_layer_set": round(value / (hbm_peak * world), 4),
+    }
+    if details:
+        out["details"] = details
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak):
+    """BASELINE metric in full: us / GB/s / % HBM at M = 1..16 (NVFP4 + MXFP4) and
+    TFLOPS / % peak at M >= 1024, per shape.  Outside the headline timed region."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = {"decode_nvfp4_bf16": [], "prefill_nvfp4_bf16": [], "decode_mxfp4_bf16": []}
+    g = torch.Generator(device=dev).manual_seed(7)
+    names = [x[0] for x in layers[0]]
+
+    def timed(fn, reps):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    for nm, n, k, _, _, _ in layers[0]:
+        idx = names.index(nm)
+        for m in (1, 4, 8, 16):
+            a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)
+            us = timed(lambda i: pk.mul_nvfp4_a16(a, layers[i % copies][idx][4], layers[i % copies][idx][5],
+                                                  gs, m, n, k, -1), 20)
+            by = algo_bytes(m, n, k)
+            res["decode_nvfp4_bf16"].append({"gemm": nm, "m": m, "us": round(us, 2),
+                                             "gbs": round(by / us * 1e-3), "frac_hbm": round(by / us * 1e-3 / hbm_peak, 3)})
+        for m in (1024, 4096):
+            a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)
+            us = timed(lambda i: pk.mul_nvfp4_a16(a, layers[i % copies][idx][4], layers[i % copies][idx][5],
+                                                  gs, m, n, k, -1), 5)
+            tf = 2.0 * m * n * k / us * 1e-6
+            res["prefill_nvfp4_bf16"].append({"gemm": nm, "m": m, "us": round(us, 1),
+                                              "tflops": round(tf, 1), "frac_bf16_peak": round(tf / tf_peak, 3)})
+    # MXFP4 (config 3) on the two mid-sized shapes
+    for nm, n, k in (("qkv", 10240, 8192), ("down", 8192, 28672)):
+        packs = []
+        for _ in range(3):
+            q = torch.randint(0, 256, (n, k // 2), generator=g, dtype=torch.uint8, device=dev)
+            s = torch.randint(110, 130, (n, k // 32), generator=g, dtype=torch.uint8, device=dev)
+            packs.append((pk.repack_mxfp4(q.view(torch.int32), n, k), pk.process_mxfp4_scales(s, n, k)))
+        for m in (1, 16):
+            a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)
+            us = timed(lambda i: pk.mul_mxfp4_a16(a, packs[i % 3][0], packs[i % 3][1], gs, m, n, k, -1), 20)
+            by = algo_bytes(m, n, k, 32)
+            res["decode_mxfp4_bf16"].append({"gemm": nm, "m": m, "us": round(us, 2), "gbs": round(by / us * 1e-3),
+                                             "frac_hbm": round(by / us * 1e-3 / hbm_peak, 3)})
+    return res
+
+
+if __name__ == "__main__":
+    main()

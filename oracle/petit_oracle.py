@@ -151,6 +151,24 @@ def nvfp4_gemm_ref(a: torch.Tensor, q_u8: torch.Tensor, scales_e4m3: torch.Tenso
     return gemm_ref(a.cpu(), b_ref)
 
 
+def nvfp4_gemm_ref_torch(a: torch.Tensor, q_u8: torch.Tensor, scales_e4m3: torch.Tensor,
+                         global_scale: torch.Tensor) -> torch.Tensor:
+    """Same computation as nvfp4_gemm_ref with torch ops only (multi-threaded on the
+    host), statement for statement what tests/ops/test_fp4_gemm_quark.py:9-24,51-53
+    does; used as the timed CPU baseline."""
+    lut = torch.from_numpy(E2M1_VALUES)
+    q_u8 = q_u8.cpu()
+    lo = q_u8 & 0x0F
+    hi = q_u8 >> 4
+    deq = torch.empty((q_u8.size(0), q_u8.size(1) * 2), dtype=torch.float32)
+    deq[:, 0::2] = lut[lo.long()]
+    deq[:, 1::2] = lut[hi.long()]
+    w = (deq.view(q_u8.size(0), -1, NVFP4_GROUP) * scales_e4m3.cpu().float().unsqueeze(-1)
+         ).view(q_u8.size(0), -1)
+    b_ref = w * float(global_scale.item())
+    return gemm_ref(a.cpu(), b_ref)
+
+
 def mxfp4_gemm_ref(a: torch.Tensor, q_u8: torch.Tensor, scales_e8m0: torch.Tensor,
                    global_scale: torch.Tensor) -> torch.Tensor:
     """tests/ops/test_fp4_gemm_quark.py:83-87: dequantise to bf16, fp32 matmul,

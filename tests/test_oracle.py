@@ -58,6 +58,7 @@ def test_nvfp4_gemm_ref_matches_reference_oracle(m, n, k, seed):
     assert np.allclose([w.astype(np.float64).sum(), np.abs(w).astype(np.float64).sum()],
                        g[f"{tag}_wsum"], rtol=0, atol=0)
     c = orc.nvfp4_gemm_ref(a, q, s, gs)
+    assert torch.equal(orc.nvfp4_gemm_ref_torch(a, q, s, gs), c)  # the timed CPU baseline
     c_gold = from_bits16(g[f"{tag}_c"], torch.bfloat16)
     # same torch fp32 matmul on the same machine class: identical up to 1 bf16 ulp
     torch.testing.assert_close(c.float(), c_gold.float(), rtol=8e-3, atol=1e-3)

@@ -206,11 +206,11 @@ def main():
     acts = {k: torch.randn((m, k), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
             for k in {k for _, _, k, _ in shard}}
 
-    def layer_step(i, a_by_k=acts):
+    def layer_step(i, a_by_k=acts, collective=True):
         outs = []
         for nm, n, k, kind, b, sp in layers[i % copies]:
             c = pk.mul_nvfp4_a16(a_by_k[k], b, sp, gs, m, n, k, -1)
-            if kind == "row" and world > 1:
+            if kind == "row" and world > 1 and collective:
                 dist.all_reduce(c)
             outs.append(c)
         return outs
@@ -245,7 +245,7 @@ def main():
         t_end = time.time() + 0.25
         i = 0
         while time.time() < t_end:
-            layer_step(i)
+            layer_step(i, collective=False)  # rank-local load only: no unmatched collectives
             i += 1
         torch.cuda.synchronize()
         hi = sampler.mark()

@@ -80,6 +80,9 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     // Small-N MMAs that accumulate into the same TMEM columns serialise on the
     // full MMA latency (~130 clk measured), so consecutive k-steps rotate over
     // kChains independent accumulators that the epilogue sums.
+    // (Measured: 8 chains with a single accumulator buffer is slower than 4 chains
+    // double-buffered -- the segment-boundary stall costs more than the extra chains
+    // gain.)
     static constexpr int kNumAcc = (NTOK <= 32 || NTOK == 128) ? 2 : 1;
     static constexpr int kChains = NTOK >= 128 ? 1 : 128 / (kNumAcc * NTOK);
     static_assert((KS / 32) % kKSlices == 0, "chunks must split evenly over the k-slices");
@@ -414,15 +417,49 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             const uint32_t m_valid = args.m - m0 < (uint32_t)NTOK ? args.m - m0 : NTOK;
             const bool row_ok = row < rows;
 
-            // partial-tile bookkeeping
-            const uint32_t tile_u0 = g.tile * sched.k_tiles;
-            const uint32_t b_first = sched.owner(tile_u0);
-            const uint32_t b_last = sched.owner(tile_u0 + sched.k_tiles - 1);
-            const uint32_t my_slot =
-                blockIdx.x * 2 + ((u == u_begin) ? 0u : 1u);
-            float *slot = args.ws_partials + (size_t)my_slot * (kTileN * NTOK);
+            // Split tiles (stream-K): the CTA that owns the FIRST k-part of a tile
+            // reaches it as the last segment of its range, after every other
+            // contributor (which meets the tile at the START of its range) has
+            // published its fp32 partial.  So that CTA is the reducer: it adds the
+            // published partials to its own accumulator in CTA order (deterministic)
+            // and writes the output; contributors never wait.
+            const bool is_reducer = !full_k && g.kt0 == 0;
+            const bool is_contrib = !full_k && g.kt0 != 0;
+            float *slot = args.ws_partials + (size_t)blockIdx.x * (kTileN * NTOK);
+            uint32_t b_first = blockIdx.x, b_last = blockIdx.x;
+            if (is_reducer) b_last = sched.owner(g.tile * sched.k_tiles + sched.k_tiles - 1);
 
-            while (!mbar_try_wait(&bars->acc_full[acc], acc_ph)) __nanosleep(128);
+            // Reducer: the other contributors published long ago, so their partials
+            // for the first 16 tokens are summed (in CTA order) into registers while
+            // the MMAs of this last segment are still running; the tail after
+            // acc_full is then just TMEM read + add + store.
+            float pre[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pre[j] = 0.f;
+            if (is_reducer) {
+                if (ew_tid == 0) {
+                    const uint32_t need = b_last - b_first;
+                    uint32_t seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
+                                     : "=r"(seen)
+                                     : "l"(args.ws_counters + g.tile)
+                                     : "memory");
+                    } while (seen < need);
+                }
+                named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
+#pragma unroll 1
+                for (uint32_t b = b_first + 1; b <= b_last; ++b) {
+                    const float *p = args.ws_partials + (size_t)b * (kTileN * NTOK) + row;
+                    float x[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        x[j] = (uint32_t)j < m_valid ? __ldcg(p + (size_t)j * kTileN) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pre[j] += x[j];
+                }
+            }
+            while (!mbar_try_wait(&bars->acc_full[acc], acc_ph)) __nanosleep(32);
             tc_fence_after();
             if (ew_tid == 0 && u + (g.kt1 - g.kt0) >= u_end) trace_stamp(args, 6);
 #pragma unroll 1
@@ -444,21 +481,49 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
                 }
-                if (full_k) {
-                    if (row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const uint32_t t = c0 + j;
-                            if (t < m_valid)
-                                store_out<C::kIsBf16>(args.c, (size_t)(m0 + t) * args.n + n_idx,
-                                                      v[j] * gs);
-                        }
-                    }
-                } else {
+                if (is_contrib) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if ((uint32_t)(c0 + j) < m_valid)
                             __stcg(&slot[(size_t)(c0 + j) * kTileN + row], v[j]);
+                    continue;
+                }
+                if (is_reducer && c0 == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += pre[j];
+                } else if (is_reducer && row_ok) {
+                    // all loads of a pass are issued before the first add: one L2
+                    // round trip per pass of up to kSeg partials
+                    constexpr int kSeg = 3;
+#pragma unroll 1
+                    for (uint32_t bb = b_first + 1; bb <= b_last; bb += kSeg) {
+                        float x[kSeg][16];
+#pragma unroll
+                        for (int sg = 0; sg < kSeg; ++sg) {
+                            const bool seg_ok = bb + sg <= b_last;
+                            const float *p = args.ws_partials +
+                                             (size_t)(seg_ok ? bb + sg : b_last) * (kTileN * NTOK) +
+                                             (size_t)c0 * kTileN + row;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                x[sg][j] = (seg_ok && (uint32_t)(c0 + j) < m_valid)
+                                               ? __ldcg(p + (size_t)j * kTileN)
+                                               : 0.f;
+                        }
+#pragma unroll
+                        for (int sg = 0; sg < kSeg; ++sg)
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += x[sg][j];
+                    }
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const uint32_t t = c0 + j;
+                        if (t < m_valid)
+                            store_out<C::kIsBf16>(args.c, (size_t)(m0 + t) * args.n + n_idx,
+                                                  v[j] * gs);
+                    }
                 }
             }
             // accumulator drained -> MMA may reuse it
@@ -466,68 +531,16 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
 
-            if (!full_k) {
-                // publish the partial: CTA barrier, then one release-atomic on the tile
-                // counter (cumulative over the barrier); the last CTA to arrive acquires.
+            if (is_contrib) {
+                // publish: CTA barrier, then one release-increment of the tile counter
                 named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
-                if (ew_tid == 0) {
-                    uint32_t old;
-                    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;"
-                                 : "=r"(old)
-                                 : "l"(args.ws_counters + g.tile)
+                if (ew_tid == 0)
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(
+                                     args.ws_counters + g.tile)
                                  : "memory");
-                    bars->flag = old;
-                }
+            } else if (is_reducer) {
                 named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
-                const uint32_t old = bars->flag;
-                const uint32_t nseg = b_last - b_first + 1;
-                if (old == nseg - 1) {
-                    // last to arrive: reduce all partials in CTA order (deterministic).
-                    // All loads of a pass are issued before the first add so the pass
-                    // costs one L2 round trip.
-                    if (row_ok) {
-                        constexpr int kU = 8, kSeg = 4;
-#pragma unroll 1
-                        for (uint32_t t0 = 0; t0 < m_valid; t0 += kU) {
-                            float sum[kU];
-#pragma unroll
-                            for (int j = 0; j < kU; ++j) sum[j] = 0.f;
-#pragma unroll 1
-                            for (uint32_t bb = b_first; bb <= b_last; bb += kSeg) {
-                                float x[kSeg][kU];
-#pragma unroll
-                                for (int sg = 0; sg < kSeg; ++sg) {
-                                    const uint32_t b = bb + sg;
-                                    const bool seg_ok = b <= b_last;
-                                    const uint32_t bc = seg_ok ? b : b_last;
-                                    const uint32_t sl =
-                                        bc * 2 + ((sched.begin(bc) / sched.k_tiles) == g.tile ? 0u : 1u);
-                                    const float *p = args.ws_partials +
-                                                     (size_t)sl * (kTileN * NTOK) +
-                                                     (size_t)t0 * kTileN + row;
-#pragma unroll
-                                    for (int j = 0; j < kU; ++j)
-                                        x[sg][j] = (seg_ok && t0 + j < m_valid)
-                                                       ? __ldcg(p + (size_t)j * kTileN)
-                                                       : 0.f;
-                                }
-#pragma unroll
-                                for (int sg = 0; sg < kSeg; ++sg)
-#pragma unroll
-                                    for (int j = 0; j < kU; ++j) sum[j] += x[sg][j];
-                            }
-#pragma unroll
-                            for (int j = 0; j < kU; ++j)
-                                if (t0 + j < m_valid)
-                                    store_out<C::kIsBf16>(
-                                        args.c, (size_t)(m0 + t0 + j) * args.n + n_idx,
-                                        sum[j] * gs);
-                        }
-                    }
-                    if (ew_tid == 0) args.ws_counters[g.tile] = 0; // self-cleaning
-                }
-                // flag is reused by the next partial segment
-                named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
+                if (ew_tid == 0) args.ws_counters[g.tile] = 0; // self-cleaning
             }
             u += g.kt1 - g.kt0;
         }
@@ -616,7 +629,7 @@ template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
 } // namespace
 
 size_t workspace_partials_bytes() {
-    return (size_t)kMaxGrid * 2 * kTileN * 256 * sizeof(float);
+    return (size_t)kMaxGrid * kTileN * 256 * sizeof(float);
 }
 size_t workspace_counters_bytes() { return (size_t)kMaxTiles * sizeof(unsigned); }
 

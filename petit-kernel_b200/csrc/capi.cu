@@ -31,7 +31,7 @@ constexpr uint64_t kMfmaF16 = 0, kMfmaBf16 = 1;
 constexpr int kTokVariants[] = {16, 32, 64, 128, 256};
 constexpr int kNumVariants = 5;
 
-constexpr int stage_k_for(int ntok) { return ntok <= 64 ? 256 : 128; }
+constexpr int stage_k_for(int ntok) { return ntok <= 64 ? 256 : (ntok == 128 ? 128 : 64); }
 
 constexpr uint64_t make_solution(int ntok, uint64_t elem_b, uint64_t mfma) {
     return (uint64_t)(ntok / 16)                              // tile_m  [0,8)
@@ -60,15 +60,22 @@ bool decode_solution(uint64_t id, Decoded *d) {
     return id == make_solution(d->ntok, d->elem_b, d->mfma);
 }
 
-int default_ntok(unsigned m) {
+// Default solution (the role of ChooseDefaultFp4Fp16Solution, algo_chooser.cc:64-132):
+// the smallest token tile that holds M up to 128 tokens; beyond that 256-token tiles
+// only once there are enough of them (>= 8 per SM) to amortise their longer
+// prologue/epilogue -- measured on the 70B shapes (gpurun_out bench27: qkv M=1024
+// 58 % of peak with 128-token tiles vs 49 % with 256; gate_up 70 % vs 68 %).
+int default_ntok(unsigned m, unsigned n) {
     if (const char *e = std::getenv("PETIT_FORCE_NTOK")) {
         int v = std::atoi(e);
         for (int t : kTokVariants)
             if (t == v) return v;
     }
     for (int t : kTokVariants)
-        if (m <= (unsigned)t) return t;
-    return 256;
+        if (t <= 128 && m <= (unsigned)t) return t;
+    const unsigned long long tiles256 =
+        (unsigned long long)((n + layout::kTileN - 1) / layout::kTileN) * ((m + 255) / 256);
+    return tiles256 >= 8ull * 148 ? 256 : 128;
 }
 
 bool problem_shape_ok(unsigned n, unsigned k) {
@@ -142,7 +149,7 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
         if (!problem_shape_ok(n, k)) return PETIT_ERROR_PROBLEM_SHAPE;
         if (hints->a_type != PETIT_DTYPE_FP16 && hints->a_type != PETIT_DTYPE_BF16)
             return PETIT_ERROR_PROBLEM_SHAPE;
-        d.ntok = default_ntok(m);
+        d.ntok = default_ntok(m, n);
         d.elem_b = is_mx ? kElemMx : kElemNv;
         d.mfma = hints->a_type == PETIT_DTYPE_BF16 ? kMfmaBf16 : kMfmaF16;
     } else {
@@ -180,6 +187,18 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
     args.two29 = 1u << 29;
     args.add64 = 0x70007000ull << 32;
     args.trace = g_trace;
+    {
+        static const int pdl = [] {
+            const char *e = std::getenv("PETIT_PDL");
+            return e ? std::atoi(e) : 1;
+        }();
+        args.use_pdl = (uint32_t)pdl;
+        static const int dbg = [] {
+            const char *e = std::getenv("PETIT_DEBUG_FLAGS");
+            return e ? std::atoi(e) : 0;
+        }();
+        args.debug_flags = (uint32_t)dbg;
+    }
     {
         static const int skew = [] {
             const char *e = std::getenv("PETIT_SKEW");

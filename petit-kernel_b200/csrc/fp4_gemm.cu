@@ -44,11 +44,16 @@ using namespace petit::dq;
 namespace {
 
 // Warp roles, aligned to warpgroups so setmaxnreg can rebalance registers:
-//   WG0: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-3 idle
-//   WG1: warps 4-7  = epilogue (one per TMEM lane quarter)
+//   WG0:   warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-3 idle
+//   WG1:   warps 4-7  = epilogue (one per TMEM lane quarter)
 //   WG2-5: warps 8-23 = dequant (4 per lane quarter -> 4 per SM sub-partition)
+// (Measured: putting the two single-thread roles on the highest warp ids instead
+// makes decode ~20 % slower -- their mbarrier polling then wins arbitration
+// against the dequant warps.)
 constexpr int kNumDequantWarps = 16;
 constexpr int kNumEpilogueWarps = 4;
+constexpr int kProducerWarp = 0;
+constexpr int kMmaWarp = 1;
 constexpr int kFirstEpilogueWarp = 4;
 constexpr int kFirstDequantWarp = 8;
 constexpr int kNumWarps = kFirstDequantWarp + kNumDequantWarps;
@@ -85,7 +90,15 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     // gain.)
     static constexpr int kNumAcc = (NTOK <= 32 || NTOK == 128) ? 2 : 1;
     static constexpr int kChains = NTOK >= 128 ? 1 : 128 / (kNumAcc * NTOK);
-    static_assert((KS / 32) % kKSlices == 0, "chunks must split evenly over the k-slices");
+    // When a stage has fewer chunks than k-slice warps (KS = 64), the warps form
+    // kGroups groups that take alternate stages.
+    // Prefill tiles (NTOK >= 128) are tensor-bound: only half of the dequant warps
+    // work there, the rest would just compete with the MMA issuer for issue slots.
+    static constexpr int kUsedSlices = NTOK >= 128 ? kKSlices / 2 : kKSlices;
+    static constexpr int kGroups = kUsedSlices > kChunks ? kUsedSlices / kChunks : 1;
+    static constexpr int kActiveSlices = kUsedSlices / kGroups;  // k-slice warps per stage
+    static constexpr int kStageWarps = 4 * kActiveSlices;        // dequant warps per stage
+    static_assert(kChunks % kActiveSlices == 0, "chunks must split evenly over the k-slices");
     static constexpr int kAccBufCols = kChains * NTOK;
     static constexpr int kAccCols = kNumAcc * kAccBufCols;
     static_assert(KS / 16 >= kChains, "stage must cover every accumulator chain");
@@ -148,11 +161,36 @@ __device__ __forceinline__ void trace_stamp(const GemmArgs &args, int slot) {
         args.trace[blockIdx.x * 16 + slot] = t;
     }
 }
+// Experiment hooks (per-stage timeline, PETIT_DEBUG_FLAGS knock-outs) cost ~20 % in the
+// hot loops, so they only exist when compiled with -DPETIT_DEBUG_HOOKS.
+#ifdef PETIT_DEBUG_HOOKS
+#define PETIT_DBG(flags, bit) ((flags) & (bit))
+#else
+#define PETIT_DBG(flags, bit) false
+#endif
+// Per-stage timeline of CTA 0 (debug): slots [160*16 + stage*8 + ev], stage < 64.
+__device__ __forceinline__ void trace_stage(const GemmArgs &args, uint32_t stage, int ev) {
+#ifndef PETIT_DEBUG_HOOKS
+    (void)args; (void)stage; (void)ev;
+    return;
+#endif
+    if (args.trace && blockIdx.x == 0 && stage < 64) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        args.trace[160 * 16 + stage * 8 + ev] = t;
+    }
+}
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+__device__ __forceinline__ void griddep_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     uint4 v;
@@ -200,6 +238,9 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
 
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     if (threadIdx.x == 0) trace_stamp(args, 0);
+    // Let the next kernel on the stream (if it was launched with programmatic stream
+    // serialisation) start its prologue / weight prefetch on SMs as they free up.
+    if (threadIdx.x == 0) griddep_launch_dependents();
 
     Sched sched;
     sched.k_tiles = args.k / kTileK;
@@ -210,14 +251,14 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
     const uint32_t u_begin = sched.begin(blockIdx.x);
     const uint32_t u_end = sched.begin(blockIdx.x + 1);
 
-    if (warp == 0 && lane == 0) {
+    if (warp == kProducerWarp && lane == 0) {
         prefetch_tensormap(&tmap_act);
         for (int i = 0; i < C::kStages; ++i) {
             mbar_init(&bars->full[i], 1);
-            mbar_init(&bars->empty[i], kNumDequantWarps + 1);
+            mbar_init(&bars->empty[i], C::kStageWarps + 1);
         }
         for (int i = 0; i < C::kAStages; ++i) {
-            mbar_init(&bars->a_full[i], kNumDequantWarps);
+            mbar_init(&bars->a_full[i], C::kStageWarps);
             mbar_init(&bars->a_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -226,65 +267,105 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+    if (warp == kMmaWarp) tmem_alloc(&bars->tmem_base, 512);
     tc_fence_before();
-    // Warp 0 initialised the barriers itself, so it only signals the setup barrier
-    // and starts streaming weights while the other warps wait for the TMEM base.
-    if (warp == 0) {
+    // The producer warp initialised the barriers itself, so it only signals the setup
+    // barrier and starts streaming weights while the others wait for the TMEM base.
+    if (warp == kProducerWarp) {
         __syncwarp();
         asm volatile("bar.arrive %0, %1;" ::"n"(kSetupBarId), "n"(kNumThreads) : "memory");
     } else {
         named_bar_sync(kSetupBarId, kNumThreads);
     }
     tc_fence_after();
-    const uint32_t tmem = warp == 0 ? 0u : bars->tmem_base;
+    const uint32_t tmem = warp == kProducerWarp ? 0u : bars->tmem_base;
     const uint32_t tmem_a0 = tmem + C::kAccCols;
     if (threadIdx.x == 0) trace_stamp(args, 1);
 
     const uint32_t k_bytes_half = args.k / 2;
 
     if (warp < kFirstEpilogueWarp) setmaxnreg_dec<kRegsLight>();
-    if (warp == 0) {
+    if (warp == kProducerWarp) {
         // ===================== TMA producer =====================
         // The loop is executed by the whole (converged) warp so that every value is
         // warp-uniform; only the async instructions are issued by one elected lane.
+        //
+        // Programmatic dependent launch: weights and scales are constants, so the
+        // first ring-full of them is requested BEFORE griddepcontrol.wait, i.e. while
+        // the previous kernel on the stream is still draining; everything that may
+        // depend on that kernel (the token tile here, global_scale / workspace /
+        // output in the epilogue warps) is touched only after the wait.
         const uint64_t pol_stream = policy_evict_first();
-        uint32_t it = 0;
-        for (uint32_t u = u_begin; u < u_end;) {
-            const Segment g = make_segment(sched, u, u_end);
-            const uint32_t rows = tile_rows(args.n, g.n_tile);
-            const uint8_t *w_tile = args.w + (size_t)g.n_tile * kTileN * k_bytes_half;
-            const uint8_t *sc_tile =
-                args.sc + (size_t)g.n_tile * kTileN * (args.k / 64) * C::kScPerSub;
-            const uint32_t w_stage_bytes = C::kChunks * rows * 16;
-            const uint32_t sc_stage_bytes = C::kSubs * rows * C::kScPerSub;
-            const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
-            const uint8_t *w_src = w_tile + (size_t)g.kt0 * rows * 128;
-            const uint8_t *sc_src = sc_tile + (size_t)g.kt0 * rows * 4 * C::kScPerSub;
-            int32_t k_slab = (int32_t)(g.kt0 * 4);
-            for (uint32_t i = 0; i < n_stage; ++i, ++it) {
-                const uint32_t s = it % C::kStages;
-                const uint32_t ph = (it / C::kStages) & 1;
-                mbar_wait(&bars->empty[s], ph ^ 1);
-                if (elect_one()) {
-                    uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
-                    mbar_arrive_expect_tx(&bars->full[s],
-                                          C::kActBytes + w_stage_bytes + sc_stage_bytes);
-                    bulk_g2s_hint(st + C::kActBytes, w_src, w_stage_bytes, &bars->full[s],
-                                  pol_stream);
-                    bulk_g2s_hint(st + C::kActBytes + C::kWBytes, sc_src, sc_stage_bytes,
-                                  &bars->full[s], pol_stream);
-                    // token tile: box {64 k, NTOK tokens, kSubs slabs}
-                    tma_load_3d(st, &tmap_act, &bars->full[s], 0, g.m_tile * NTOK, k_slab);
-                }
-                __syncwarp();
-                w_src += w_stage_bytes;
-                sc_src += sc_stage_bytes;
-                k_slab += C::kSubs;
+        const uint32_t total_stages = (u_end - u_begin) * C::kStagesPerUnit;
+        const uint32_t early = total_stages < (uint32_t)C::kStages ? total_stages : C::kStages;
+        // pass 0: weights+scales of stages [0, early); pass 1: token tiles of the same
+        // stages (after the grid dependency resolved); pass 2: the rest, both.
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+            if (pass == 1) {
+                griddep_wait();
+                if (lane == 0) trace_stamp(args, 2);
             }
-            u += g.kt1 - g.kt0;
+            const uint32_t it_lo = pass == 2 ? early : 0u;
+            const uint32_t it_hi = pass == 2 ? total_stages : early;
+            const bool do_w = pass != 1, do_act = pass != 0;
+            uint32_t it = 0;
+            for (uint32_t u = u_begin; u < u_end && it < it_hi;) {
+                const Segment g = make_segment(sched, u, u_end);
+                const uint32_t rows = tile_rows(args.n, g.n_tile);
+                const uint8_t *w_tile = args.w + (size_t)g.n_tile * kTileN * k_bytes_half;
+                const uint8_t *sc_tile =
+                    args.sc + (size_t)g.n_tile * kTileN * (args.k / 64) * C::kScPerSub;
+                const uint32_t w_stage_bytes = C::kChunks * rows * 16;
+                const uint32_t sc_stage_bytes = C::kSubs * rows * C::kScPerSub;
+                const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
+                const uint8_t *w_src = w_tile + (size_t)g.kt0 * rows * 128;
+                const uint8_t *sc_src = sc_tile + (size_t)g.kt0 * rows * 4 * C::kScPerSub;
+                int32_t k_slab = (int32_t)(g.kt0 * 4);
+                for (uint32_t i = 0; i < n_stage && it < it_hi; ++i, ++it) {
+                    if (it >= it_lo) {
+                        const uint32_t s = it % C::kStages;
+                        const uint32_t ph = (it / C::kStages) & 1;
+                        if (pass == 2) mbar_wait(&bars->empty[s], ph ^ 1);
+                        if (elect_one()) {
+                            uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
+                            trace_stage(args, it, do_w ? 0 : 1);
+                            if (do_w) {
+                                mbar_arrive_expect_tx(&bars->full[s], C::kActBytes + w_stage_bytes +
+                                                                          sc_stage_bytes);
+                                bulk_g2s_hint(st + C::kActBytes, w_src, w_stage_bytes,
+                                              &bars->full[s], pol_stream);
+                                if (PETIT_DBG(args.debug_flags, 8u)) // experiment: no scale copy
+                                    asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(
+                                                     smem_u32(&bars->full[s])),
+                                                 "r"(sc_stage_bytes)
+                                                 : "memory");
+                                else
+                                bulk_g2s_hint(st + C::kActBytes + C::kWBytes, sc_src,
+                                              sc_stage_bytes, &bars->full[s], pol_stream);
+                            }
+                            // token tile: box {64 k, NTOK tokens, kSubs slabs}
+                            if (do_act) {
+                                if (PETIT_DBG(args.debug_flags, 4u)) // experiment: no token-tile traffic
+                                    asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(
+                                                     smem_u32(&bars->full[s])),
+                                                 "r"((uint32_t)C::kActBytes)
+                                                 : "memory");
+                                else
+                                    tma_load_3d(st, &tmap_act, &bars->full[s], 0, g.m_tile * NTOK,
+                                                k_slab);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    w_src += w_stage_bytes;
+                    sc_src += sc_stage_bytes;
+                    k_slab += C::kSubs;
+                }
+                u += g.kt1 - g.kt0;
+            }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_f16(
             C::kIsBf16 ? kFmtBF16 : kFmtF16, C::kIsBf16 ? kFmtBF16 : kFmtF16, 128, NTOK);
@@ -306,13 +387,13 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                 mbar_wait(&bars->full[s], ph);      // token tile landed
                 mbar_wait(&bars->a_full[ta], ta_ph); // weights are in TMEM
                 tc_fence_after();
+                if (lane == 0) trace_stage(args, it, 5);
                 if (elect_one()) {
                     const uint64_t bdesc_s = bdesc0 + (uint64_t)((s * C::kStageBytes) >> 4);
                     const uint32_t a_tmem = tmem_a0 + ta * C::kACols;
 #pragma unroll
                     for (int j = 0; j < KS / 16; ++j) {
-                        constexpr int kDummy = 0;
-                        (void)kDummy;
+                        if (PETIT_DBG(args.debug_flags, 1u) && j != 0) continue; // experiment: 1 MMA/stage
                         const uint64_t bdesc =
                             bdesc_s + (uint64_t)(((j / 4) * (NTOK * 128) + (j % 4) * 32) >> 4);
                         mma_f16_ts(d_tmem + (j % C::kChains) * NTOK, a_tmem + j * 8, bdesc,
@@ -321,26 +402,34 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                     tc_commit(&bars->a_empty[ta]);
                     tc_commit(&bars->empty[s]);
                     if (i + 1 == n_stage) tc_commit(&bars->acc_full[acc]);
+                    trace_stage(args, it, 6);
                 }
                 __syncwarp();
             }
             u += g.kt1 - g.kt0;
         }
         if (lane == 0) trace_stamp(args, 5);
-    } else if (warp >= kFirstDequantWarp) {
+    } else if (warp >= kFirstDequantWarp &&
+               (warp - kFirstDequantWarp) / 4 < (uint32_t)C::kUsedSlices) {
         // ===================== dequant warps =====================
         setmaxnreg_inc<kRegsDequant>();
         const uint32_t dw = warp - kFirstDequantWarp;
         const uint32_t quarter = warp % 4;     // TMEM lane quarter this warp may touch
         const uint32_t kslice = dw / 4;        // which slice of the stage's k range
         const uint32_t row = quarter * 32 + lane;
-        constexpr int kMyChunks = C::kChunks / kKSlices;
+        constexpr int kMyChunks = C::kChunks / C::kActiveSlices;
         constexpr int kScBytesPerChunk = C::kScPerSub / 2; // NV: 2 bytes, MX: 1 byte
         constexpr int kMyScBytes = kMyChunks * kScBytesPerChunk;
-        const uint32_t c0 = kslice * kMyChunks;            // first chunk of this thread
+        const uint32_t group = kslice / C::kActiveSlices;  // which alternate stages are mine
+        const uint32_t c0 = (kslice % C::kActiveSlices) * kMyChunks; // first chunk of this thread
         const uint32_t w_base = smem_u32(stage_base) + C::kActBytes;
         const uint32_t tmem_dst = tmem_a0 + ((quarter * 32) << 16) + c0 * 16;
         uint32_t s = 0, ph = 0, ta = 0, ta_ph = 1; // ta_ph: parity to wait on a_empty
+        uint32_t it_dbg = 0;
+        if (args.trace && threadIdx.x == kFirstDequantWarp * 32) {
+            mbar_wait(&bars->full[0], 0);
+            trace_stamp(args, 3);
+        }
         // The four k-slice warps of a lane quarter share one SM sub-partition and run
         // identical code; in lockstep they all hit the ALU-heavy (F2FP/LOP3) and the
         // FMA-heavy (IMAD.HI/HMUL2) parts of the loop body together and each pipe
@@ -362,8 +451,15 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                                     (c0 & 1) * kScBytesPerChunk;
             const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
             for (uint32_t i = 0; i < n_stage; ++i) {
+                if (C::kGroups > 1 && (it_dbg % C::kGroups) != group) {
+                    ++it_dbg;
+                    if (++s == C::kStages) { s = 0; ph ^= 1; }
+                    if (++ta == C::kAStages) { ta = 0; ta_ph ^= 1; }
+                    continue;
+                }
                 const uint32_t st = w_base + s * C::kStageBytes;
                 mbar_wait(&bars->full[s], ph);
+                if (threadIdx.x == kFirstDequantWarp * 32) trace_stage(args, it_dbg, 2);
                 uint4 q[kMyChunks];
 #pragma unroll
                 for (int ci = 0; ci < kMyChunks; ++ci) q[ci] = lds_v4(st + w_off + ci * rows * 16);
@@ -374,6 +470,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                 // the previous occupant of this TMEM A stage must have been consumed
                 mbar_wait(&bars->a_empty[ta], ta_ph);
                 tc_fence_after();
+                if (threadIdx.x == kFirstDequantWarp * 32) trace_stage(args, it_dbg, 3);
 #pragma unroll
                 for (int ci = 0; ci < kMyChunks; ++ci) {
                     const uint32_t bits = scbits >> (ci * 8 * kScBytesPerChunk);
@@ -381,12 +478,19 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                     if (C::kIsMx) two_step = __any_sync(0xffffffffu, mx_needs_two_step(bits));
                     const uint32_t mult = chunk_multiplier<MODE>(bits, two_step);
                     uint32_t out[16];
+                    if (PETIT_DBG(args.debug_flags, 2u)) { // experiment: no dequant math
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) out[j] = q[ci].x + j;
+                    } else
                     dequant_chunk<MODE>(q[ci], mult, two_step, out);
+                    if (!PETIT_DBG(args.debug_flags, 16u)) // experiment: no TMEM stores
                     tmem_st_x16(tmem_dst + ta * C::kACols + ci * 16, out);
                 }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
+                if (threadIdx.x == kFirstDequantWarp * 32) trace_stage(args, it_dbg, 4);
+                ++it_dbg;
                 if (lane == 0) {
                     mbar_arrive(&bars->a_full[ta]);
                     mbar_arrive(&bars->empty[s]);
@@ -397,14 +501,15 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             u += g.kt1 - g.kt0;
         }
         if (threadIdx.x == kFirstDequantWarp * 32) trace_stamp(args, 4);
-    } else if (warp >= kFirstEpilogueWarp) {
+    } else if (warp >= kFirstEpilogueWarp && warp < kFirstDequantWarp) {
         // ===================== epilogue warps =====================
         const uint32_t quarter = warp % 4;
         const uint32_t ew_tid = threadIdx.x - kFirstEpilogueWarp * 32; // 0..127
         const uint32_t row = quarter * 32 + lane;
         const uint32_t lane_base = (quarter * 32) << 16;
+        griddep_wait(); // global_scale, workspace and C may depend on the previous kernel
         float gs = *args.global_scale;
-        gs *= epilogue_factor<MODE>(); // power of two folded out of the MX multiplier
+        gs *= epilogue_factor<MODE>(); // power of two folded out of the A operand
         uint32_t seg = 0;
         for (uint32_t u = u_begin; u < u_end; ++seg) {
             const Segment g = make_segment(sched, u, u_end);
@@ -550,7 +655,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) trace_stamp(args, 8);
-    if (warp == 1) tmem_dealloc(tmem, 512);
+    if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------
@@ -610,8 +715,18 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     const unsigned grid = (unsigned)(units < (uint64_t)num_sms ? units : (uint64_t)num_sms);
     if (m_tiles * n_tiles > kMaxTiles || grid > kMaxGrid || units >= (1ull << 31))
         return kLaunchBadShape;
-    kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmap, args);
-    return cudaGetLastError() == cudaSuccess ? kLaunchOk : kLaunchCudaError;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = args.use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap, args);
+    return e == cudaSuccess ? kLaunchOk : kLaunchCudaError;
 }
 
 template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
@@ -621,7 +736,7 @@ template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
     case 32: return launch_variant<MODE, 32, 256>(args, num_sms, stream);
     case 64: return launch_variant<MODE, 64, 256>(args, num_sms, stream);
     case 128: return launch_variant<MODE, 128, 128>(args, num_sms, stream);
-    case 256: return launch_variant<MODE, 256, 128>(args, num_sms, stream);
+    case 256: return launch_variant<MODE, 256, 64>(args, num_sms, stream);
     default: return kLaunchNoKernel;
     }
 }

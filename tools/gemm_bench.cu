@@ -52,6 +52,7 @@ int main(int argc, char **argv) {
         if (only[0] && strcmp(only, s.name) && strcmp(only, "all")) continue;
         const size_t wbytes = (size_t)s.n * s.k / 2, sbytes = (size_t)s.n * s.k / (mx ? 32 : 16);
         int copies = (int)std::max<size_t>(2, (size_t)400e6 / (wbytes + sbytes) + 1);
+        if (getenv("PETIT_COPIES")) copies = atoi(getenv("PETIT_COPIES"));
         uint8_t *w, *sc;
         CK(cudaMalloc(&w, wbytes * copies));
         CK(cudaMalloc(&sc, sbytes * copies));
@@ -128,18 +129,18 @@ int main(int argc, char **argv) {
             }
             if (getenv("PETIT_TRACE")) {
                 unsigned long long *d_tr;
-                CK(cudaMalloc(&d_tr, 160 * 16 * 8));
-                CK(cudaMemset(d_tr, 0, 160 * 16 * 8));
+                CK(cudaMalloc(&d_tr, (160 * 16 + 64 * 8) * 8));
+                CK(cudaMemset(d_tr, 0, (160 * 16 + 64 * 8) * 8));
                 petit_debug_set_trace(d_tr);
-                call(1);
+                for (int i = 0; i < 4; ++i) call(i); // back-to-back: the last launch's stamps survive
                 CK(cudaDeviceSynchronize());
                 petit_debug_set_trace(nullptr);
-                std::vector<unsigned long long> tr(160 * 16);
+                std::vector<unsigned long long> tr(160 * 16 + 64 * 8);
                 CK(cudaMemcpy(tr.data(), d_tr, tr.size() * 8, cudaMemcpyDeviceToHost));
                 unsigned long long t0 = ~0ull;
                 int nb = 0;
                 for (int b = 0; b < 160; ++b) if (tr[b * 16]) { t0 = std::min(t0, tr[b * 16]); ++nb; }
-                const char *names[9] = {"entry", "setup_done", "first_tma_issued", "first_stage_landed",
+                const char *names[9] = {"entry", "setup_done", "griddep_wait_done", "first_stage_landed",
                                         "dequant_done", "mma_issued_all", "last_acc_full", "epilogue_done", "exit"};
                 printf("  trace over %d CTAs (us since first CTA entry): event min/avg/max\n", nb);
                 for (int e = 0; e < 9; ++e) {
@@ -151,6 +152,18 @@ int main(int argc, char **argv) {
                         mn = std::min(mn, d); mx2 = std::max(mx2, d); sum += d; ++cnt;
                     }
                     if (cnt) printf("    %-20s %7.2f %7.2f %7.2f\n", names[e], mn, sum / cnt, mx2);
+                }
+                if (getenv("PETIT_TRACE_STAGES")) {
+                    printf("  CTA0 per-stage (us since CTA0 entry): w_issue act_issue | dq:full a_empty st_done | mma:a_full committed\n");
+                    unsigned long long c0 = tr[0];
+                    for (int st = 0; st < 24; ++st) {
+                        printf("   st%02d", st);
+                        for (int e = 0; e < 7; ++e) {
+                            unsigned long long v = tr[160 * 16 + st * 8 + e];
+                            if (v) printf(" %7.2f", (double)(v - c0) * 1e-3); else printf("       -");
+                        }
+                        printf("\n");
+                    }
                 }
                 cudaFree(d_tr);
             }

@@ -391,7 +391,7 @@ def sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak):
         packs = []
         for _ in range(3):
             q = torch.randint(0, 256, (n, k // 2), generator=g, dtype=torch.uint8, device=dev)
-            s = torch.randint(110, 130, (n, k // 32), generator=g, dtype=torch.uint8, device=dev)
+            s = torch.randint(108, 125, (n, k // 32), generator=g, dtype=torch.uint8, device=dev)  # 2^-19..2^-3, typical of MX weights
             packs.append((pk.repack_mxfp4(q.view(torch.int32), n, k), pk.process_mxfp4_scales(s, n, k)))
         for m in (1, 16):
             a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)

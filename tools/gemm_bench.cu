@@ -57,8 +57,8 @@ int main(int argc, char **argv) {
         CK(cudaMalloc(&w, wbytes * copies));
         CK(cudaMalloc(&sc, sbytes * copies));
         fill_kernel<<<1184, 256>>>((uint32_t *)w, wbytes * copies / 4, 1, 0xffffffffu, 0);
-        // scales: NV E5M3 bytes with e5 in [8,23] ; MX e8m0 in [112,143]
-        if (mx) fill_kernel<<<1184, 256>>>((uint32_t *)sc, sbytes * copies / 4, 2, 0x1f1f1f1fu, 0x70707070u);
+        // scales: NV E5M3 bytes with e5 in [8,15] ; MX e8m0 in [108,123] (2^-19..2^-4)
+        if (mx) fill_kernel<<<1184, 256>>>((uint32_t *)sc, sbytes * copies / 4, 2, 0x0f0f0f0fu, 0x6c6c6c6cu); // e8m0 108..123
         else fill_kernel<<<1184, 256>>>((uint32_t *)sc, sbytes * copies / 4, 2, 0x3f3f3f3fu, 0x40404040u);
         for (unsigned m : ms) {
             uint16_t *a, *c;

@@ -153,6 +153,9 @@ def workload_config(args, world):
                         f"bf16 activations, M={args.m}",
             "m": args.m, "shapes": {n: [a, b] for n, a, b, _ in LAYER},
             "parallelism": f"tp{world}" if world > 1 else "single",
+            "allreduce": getattr(args, "allreduce_kind", "none"),
+            "launch": "cuda-graph per layer step" if getattr(args, "graph", False)
+            else "eager launches on one stream, programmatic dependent launch between GEMMs",
             "l2": "weights rotate over distinct copies > 2x L2 (126 MB) between reuses"}
 
 
@@ -165,6 +168,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--m", type=int, default=16)
     ap.add_argument("--no-details", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay one captured CUDA graph per layer step instead of eager launches")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -206,14 +211,40 @@ def main():
     acts = {k: torch.randn((m, k), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
             for k in {k for _, _, k, _ in shard}}
 
+    # row-parallel outputs: ncclAllReduce over NVLink (default), or with
+    # PETIT_TP_ALLREDUCE=symm a one-shot all-reduce over peer memory (torch symmetric
+    # memory); measured equal at TP 4/8 (gpurun_out bench_tp*_{symm,nccl}.log).
+    symm = None
+    allreduce_kind = "none" if world == 1 else "nccl"
+    if world > 1 and os.environ.get("PETIT_TP_ALLREDUCE", "nccl") == "symm":
+        try:
+            symm = petit_tp.SymmAllReduce()
+            for j, (nm, n, k, kind) in enumerate(shard):
+                if kind == "row":
+                    symm.reduce(symm.buffer(m, n, torch.bfloat16, dev, j).zero_())
+            torch.cuda.synchronize()
+            allreduce_kind = "symm_mem.one_shot_all_reduce"
+        except Exception as exc:  # fall back to NCCL, loudly
+            if rank == 0:
+                print(f"[bench] symmetric-memory all-reduce unavailable ({exc}); using NCCL",
+                      file=sys.stderr)
+            symm = None
+
     def layer_step(i, a_by_k=acts, collective=True):
         outs = []
-        for nm, n, k, kind, b, sp in layers[i % copies]:
-            c = pk.mul_nvfp4_a16(a_by_k[k], b, sp, gs, m, n, k, -1)
-            if kind == "row" and world > 1 and collective:
-                dist.all_reduce(c)
+        for j, (nm, n, k, kind, b, sp) in enumerate(layers[i % copies]):
+            if kind == "row" and world > 1 and collective and symm is not None:
+                buf = symm.buffer(m, n, torch.bfloat16, dev, j)
+                pk.ops.mul_nvfp4_a16_out(buf, a_by_k[k], b, sp, gs, m, n, k, -1)
+                c = symm.reduce(buf)
+            else:
+                c = pk.mul_nvfp4_a16(a_by_k[k], b, sp, gs, m, n, k, -1)
+                if kind == "row" and world > 1 and collective:
+                    dist.all_reduce(c)
             outs.append(c)
         return outs
+
+    args.allreduce_kind = allreduce_kind
 
     def sync():
         if world > 1:
@@ -223,9 +254,40 @@ def main():
     full_bytes = sum(algo_bytes(m, n, k) for _, n, k, _ in LAYER)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
+    # ---- optional CUDA graphs (--graph): one captured layer step per weight copy.  Not the
+    # default: with PDL the eager stream is as fast at TP1 (129 vs 127 us/step measured)
+    # and capturing NCCL collectives hung at TP2 on this stack.
+    use_graph = args.graph
+    graphs = None
+    if use_graph:
+        try:
+            for i in range(copies):  # warm every path (workspace, NCCL) before capture
+                layer_step(i)
+            sync()
+            graphs = []
+            side = torch.cuda.Stream()
+            for i in range(copies):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=side):
+                    layer_step(i)
+                graphs.append(gph)
+            sync()
+        except Exception as exc:
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({exc}); timing eager launches",
+                      file=sys.stderr)
+            graphs = None
+    eager_step = layer_step
+
+    def timed_step(i):
+        if graphs is not None:
+            graphs[i % copies].replay()
+        else:
+            eager_step(i)
+
     # ---- device-resident timing
     for i in range(args.warmup):
-        layer_step(i)
+        timed_step(i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -234,7 +296,7 @@ def main():
     lo = sampler.mark()
     e0.record()
     for i in range(args.steps):
-        layer_step(i)
+        timed_step(i)
     e1.record()
     sync()
     ms = e0.elapsed_time(e1)
@@ -270,12 +332,32 @@ def main():
         for h, c in zip(host_c, outs):
             h.copy_(c, non_blocking=True)
 
+    e2e_graphs = None
+    if graphs is not None:
+        try:
+            e2e_graphs = []
+            side = torch.cuda.Stream()
+            for i in range(copies):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=side):
+                    e2e_step(i)
+                e2e_graphs.append(gph)
+            sync()
+        except Exception:
+            e2e_graphs = None
+
+    def e2e_timed(i):
+        if e2e_graphs is not None:
+            e2e_graphs[i % copies].replay()
+        else:
+            e2e_step(i)
+
     for i in range(args.warmup):
-        e2e_step(i)
+        e2e_timed(i)
     sync()
     e0.record()
     for i in range(args.steps):
-        e2e_step(i)
+        e2e_timed(i)
     e1.record()
     sync()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)

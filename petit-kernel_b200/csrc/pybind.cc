@@ -168,9 +168,23 @@ void check_gemm_operands(const torch::Tensor &A, const torch::Tensor &B, const t
 }
 
 // ---- fp4.cc:163-209 ----------------------------------------------------------
-torch::Tensor MulNvFp4A16(const torch::Tensor &A, const torch::Tensor &B, const torch::Tensor &s,
-                          const torch::Tensor &global_scale, int64_t size_m, int64_t size_n,
-                          int64_t size_k, int64_t solution_id) {
+torch::Tensor alloc_or_check_out(const c10::optional<torch::Tensor> &out, const torch::Tensor &A,
+                                 int64_t size_m, int64_t size_n) {
+    if (!out.has_value()) {
+        auto options = torch::TensorOptions().dtype(A.dtype()).device(A.device());
+        return torch::empty({size_m, size_n}, options);
+    }
+    const torch::Tensor &c = *out;
+    TORCH_CHECK(c.device() == A.device() && c.dtype() == A.dtype() && c.is_contiguous() &&
+                    c.dim() == 2 && c.size(0) == size_m && c.size(1) == size_n,
+                "out must be a contiguous [size_m, size_n] tensor of A's dtype on A's device");
+    return c;
+}
+
+torch::Tensor MulNvFp4A16Impl(const torch::Tensor &A, const torch::Tensor &B, const torch::Tensor &s,
+                              const torch::Tensor &global_scale, int64_t size_m, int64_t size_n,
+                              int64_t size_k, int64_t solution_id,
+                              const c10::optional<torch::Tensor> &out) {
     int64_t groupsize = s.size(1) ? size_k / s.size(1) : 0;
     if (groupsize != 16) {
         AT_ERROR("Only groupsize = 16 is supported. size_k = ", size_k,
@@ -180,8 +194,7 @@ torch::Tensor MulNvFp4A16(const torch::Tensor &A, const torch::Tensor &B, const 
     check_gemm_operands(A, B, s, global_scale, size_m, size_n, size_k, size_n * size_k / 16);
 
     c10::cuda::CUDAGuard guard(A.device());
-    auto options = torch::TensorOptions().dtype(A.dtype()).device(A.device());
-    torch::Tensor c = torch::empty({size_m, size_n}, options);
+    torch::Tensor c = alloc_or_check_out(out, A, size_m, size_n);
 
     PetitSolutionHints hints;
     hints.a_type = a_type;
@@ -196,10 +209,17 @@ torch::Tensor MulNvFp4A16(const torch::Tensor &A, const torch::Tensor &B, const 
     return c;
 }
 
-// ---- fp4.cc:211-260 ----------------------------------------------------------
-torch::Tensor MulMxFp4A16(const torch::Tensor &A, const torch::Tensor &B, const torch::Tensor &s,
+torch::Tensor MulNvFp4A16(const torch::Tensor &A, const torch::Tensor &B, const torch::Tensor &s,
                           const torch::Tensor &global_scale, int64_t size_m, int64_t size_n,
                           int64_t size_k, int64_t solution_id) {
+    return MulNvFp4A16Impl(A, B, s, global_scale, size_m, size_n, size_k, solution_id, c10::nullopt);
+}
+
+// ---- fp4.cc:211-260 ----------------------------------------------------------
+torch::Tensor MulMxFp4A16Impl(const torch::Tensor &A, const torch::Tensor &B, const torch::Tensor &s,
+                              const torch::Tensor &global_scale, int64_t size_m, int64_t size_n,
+                              int64_t size_k, int64_t solution_id,
+                              const c10::optional<torch::Tensor> &out) {
     TORCH_CHECK(B.size(0) == size_n / kLayoutN, "B.size(0) = ", B.size(0),
                 " is not size_n / 16 = ", size_n / kLayoutN);
     TORCH_CHECK(B.size(1) == size_k * kLayoutN / kPackFactor, "B.size(1) = ", B.size(1),
@@ -211,8 +231,7 @@ torch::Tensor MulMxFp4A16(const torch::Tensor &A, const torch::Tensor &B, const 
     check_gemm_operands(A, B, s, global_scale, size_m, size_n, size_k, size_n * size_k / 32);
 
     c10::cuda::CUDAGuard guard(A.device());
-    auto options = torch::TensorOptions().dtype(A.dtype()).device(A.device());
-    torch::Tensor c = torch::empty({size_m, size_n}, options);
+    torch::Tensor c = alloc_or_check_out(out, A, size_m, size_n);
 
     PetitSolutionHints hints;
     hints.a_type = a_type;
@@ -225,6 +244,12 @@ torch::Tensor MulMxFp4A16(const torch::Tensor &A, const torch::Tensor &B, const 
                                    static_cast<uint64_t>(solution_id), stream_of(A));
     check_status(err, size_m, size_n, size_k, solution_id);
     return c;
+}
+
+torch::Tensor MulMxFp4A16(const torch::Tensor &A, const torch::Tensor &B, const torch::Tensor &s,
+                          const torch::Tensor &global_scale, int64_t size_m, int64_t size_n,
+                          int64_t size_k, int64_t solution_id) {
+    return MulMxFp4A16Impl(A, B, s, global_scale, size_m, size_n, size_k, solution_id, c10::nullopt);
 }
 
 // ---- fp4.cc:262-283 ----------------------------------------------------------
@@ -349,6 +374,21 @@ PYBIND11_MODULE(ops, m) {
         .value("kDataTypeFp8e5m2Fnuz", PETIT_DTYPE_FP8_E5M2_FNUZ)
         .value("kDataTypeMxFp4e2m1", PETIT_DTYPE_MXFP4_E2M1)
         .export_values();
+
+    // extras: write into a caller-provided output (e.g. a symmetric-memory buffer that a
+    // one-shot all-reduce of a row-parallel layer reads in place)
+    m.def("mul_nvfp4_a16_out",
+          [](const torch::Tensor &out, const torch::Tensor &a, const torch::Tensor &b,
+             const torch::Tensor &s, const torch::Tensor &gs, int64_t sm, int64_t sn, int64_t sk,
+             int64_t sol) { return MulNvFp4A16Impl(a, b, s, gs, sm, sn, sk, sol, out); },
+          py::arg("out"), py::arg("a"), py::arg("b"), py::arg("s"), py::arg("global_scale"),
+          py::arg("size_m"), py::arg("size_n"), py::arg("size_k"), py::arg("solution_id") = -1);
+    m.def("mul_mxfp4_a16_out",
+          [](const torch::Tensor &out, const torch::Tensor &a, const torch::Tensor &b,
+             const torch::Tensor &s, const torch::Tensor &gs, int64_t sm, int64_t sn, int64_t sk,
+             int64_t sol) { return MulMxFp4A16Impl(a, b, s, gs, sm, sn, sk, sol, out); },
+          py::arg("out"), py::arg("a"), py::arg("b"), py::arg("s"), py::arg("global_scale"),
+          py::arg("size_m"), py::arg("size_n"), py::arg("size_k"), py::arg("solution_id") = -1);
 
     // extras: round-trip / bit-exactness hooks and introspection
     m.def("unpack_fp4", &UnpackFp4, "Inverse of repack_nvfp4 (test hook)");

@@ -64,6 +64,36 @@ def all_reduce_sum(c: torch.Tensor, group=None) -> torch.Tensor:
     return c
 
 
+class SymmAllReduce:
+    """One-shot all-reduce of small row-parallel outputs over NVLink peer memory
+    (torch symmetric memory).  The GEMM writes its partial [M, N] straight into a
+    symmetric buffer and `torch.ops.symm_mem.one_shot_all_reduce` reads all peers'
+    buffers in one kernel -- ~3x lower latency than ncclAllReduce at these sizes
+    (16 KiB .. 1 MiB).  Falls back to NCCL when symmetric memory is unavailable."""
+
+    def __init__(self, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.bufs = {}
+        self.ok = True
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.symm_mem = symm_mem
+        except Exception:  # pragma: no cover
+            self.ok = False
+
+    def buffer(self, m: int, n: int, dtype, device, slot: int = 0) -> torch.Tensor:
+        key = (m, n, dtype, slot)
+        if key not in self.bufs:
+            buf = self.symm_mem.empty((m, n), dtype=dtype, device=device)
+            self.symm_mem.rendezvous(buf, self.group.group_name)
+            self.bufs[key] = buf
+        return self.bufs[key]
+
+    def reduce(self, buf: torch.Tensor) -> torch.Tensor:
+        return torch.ops.symm_mem.one_shot_all_reduce(buf, "sum", self.group.group_name)
+
+
 @dataclass
 class PackedLinear:
     """One FP4 linear layer resident on the current CUDA device."""
@@ -87,10 +117,17 @@ class PackedLinear:
             b, s = pk.repack_mxfp4(qw, n, k), pk.process_mxfp4_scales(scales.cuda(), n, k)
         return cls(b, s, global_scale.cuda(), n, k, fmt, kind)
 
-    def forward(self, a: torch.Tensor, group=None, reduce: bool = True) -> torch.Tensor:
+    def forward(self, a: torch.Tensor, group=None, reduce: bool = True,
+                symm: "SymmAllReduce | None" = None, slot: int = 0) -> torch.Tensor:
         import petit_kernel as pk
 
         m = a.shape[0]
+        if self.kind == "row" and reduce and symm is not None and symm.ok:
+            out = symm.buffer(m, self.n, a.dtype, a.device, slot)
+            mul_out = (pk.ops.mul_nvfp4_a16_out if self.fmt == "nvfp4"
+                       else pk.ops.mul_mxfp4_a16_out)
+            mul_out(out, a, self.b, self.s, self.global_scale, m, self.n, self.k, -1)
+            return symm.reduce(out)
         mul = pk.mul_nvfp4_a16 if self.fmt == "nvfp4" else pk.mul_mxfp4_a16
         c = mul(a, self.b, self.s, self.global_scale, m, self.n, self.k, -1)
         if self.kind == "row" and reduce:

@@ -333,6 +333,19 @@ def test_tp_shards_match_single_gpu(pk, tp):
         assert orc.max_rel_err(got, full) <= GEMM_TOL, name
 
 
+def test_out_variant_writes_in_place(pk):
+    m, n, k = 16, 512, 1024
+    a, q, s, gs = orc.make_nvfp4_case(m, n, k, 9)
+    b, sp = pack_nvfp4(pk, q, s, n, k)
+    ac, gsc = a.cuda(), gs.cuda()
+    ref = pk.mul_nvfp4_a16(ac, b, sp, gsc, m, n, k, -1)
+    out = torch.empty((m, n), dtype=torch.bfloat16, device="cuda")
+    ret = pk.ops.mul_nvfp4_a16_out(out, ac, b, sp, gsc, m, n, k, -1)
+    assert ret.data_ptr() == out.data_ptr() and torch.equal(out, ref)
+    with pytest.raises(RuntimeError, match="out must be"):
+        pk.ops.mul_nvfp4_a16_out(out[:, :256], ac, b, sp, gsc, m, n, k, -1)
+
+
 def test_native_selftest_binary(pk):
     exe = os.path.join(ROOT, "tests", "native", "selftest")
     if not os.path.exists(exe):

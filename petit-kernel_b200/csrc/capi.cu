@@ -193,6 +193,11 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
             return e ? std::atoi(e) : 1;
         }();
         args.use_pdl = (uint32_t)pdl;
+        static const int cl = [] {
+            const char *e = std::getenv("PETIT_CLUSTER");
+            return e ? std::atoi(e) : 1;
+        }();
+        args.use_cluster = (uint32_t)cl;
         static const int dbg = [] {
             const char *e = std::getenv("PETIT_DEBUG_FLAGS");
             return e ? std::atoi(e) : 0;

@@ -122,7 +122,8 @@ template <int MODE, int NTOK, int KS> struct Cfg {
 
 struct Barriers {
     uint64_t full[16];
-    uint64_t empty[16];
+    uint64_t empty[16];     // weights/scales of the stage consumed (dequant warps)
+    uint64_t empty_act[16]; // token tile of the stage consumed (MMA commit; both CTAs if CL)
     uint64_t a_full[8];
     uint64_t a_empty[8];
     uint64_t acc_full[2];
@@ -137,6 +138,7 @@ struct Sched {
     uint32_t k_tiles, m_tiles, n_tiles;
     uint32_t total_units; // < 2^31, checked by the launcher
     uint32_t grid;
+    uint32_t n_mul, n_add; // this CTA's n-tile = n_mul * (tile / m_tiles) + n_add
 
     __device__ __forceinline__ uint32_t begin(uint32_t b) const {
         return (uint32_t)((uint64_t)total_units * b / grid);
@@ -159,7 +161,7 @@ __device__ __forceinline__ Segment make_segment(const Sched &s, uint32_t u,
     uint32_t left = u_end - u;
     uint32_t room = s.k_tiles - g.kt0;
     g.kt1 = g.kt0 + (left < room ? left : room);
-    g.n_tile = g.tile / s.m_tiles;
+    g.n_tile = s.n_mul * (g.tile / s.m_tiles) + s.n_add;
     g.m_tile = g.tile % s.m_tiles;
     return g;
 }
@@ -195,6 +197,25 @@ template <int N> __device__ __forceinline__ void setmaxnreg_inc() {
 }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::
+                     : "memory");
+}
+// 3-D tensor-map load delivered to every CTA in `mask` at the same smem / mbarrier offsets
+__device__ __forceinline__ void tma_load_3d_mc(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                               int c0, int c1, int c2, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+                 ".multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+                 : "memory");
+}
+// tcgen05.commit arriving on the same mbarrier offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster"
+                 ".b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void griddep_wait() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -235,10 +256,17 @@ __device__ __forceinline__ void store_out(void *c, size_t off, float r) {
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
-template <int MODE, int NTOK, int KS>
+// CL = true: thread-block clusters of two CTAs that work on the SAME token tile and k
+// range but on adjacent n-tiles (2p, 2p+1).  Each CTA loads half of the token tile and
+// TMA-multicasts it into both CTAs' shared memory, halving the L2->SM activation
+// traffic that bounds the prefill kernel (measured 42.7 B/clk/SM, the L2 fabric cap).
+template <int MODE, int NTOK, int KS, bool CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
     using C = Cfg<MODE, NTOK, KS>;
+    uint32_t cta_rank = 0;
+    if (CL) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const uint32_t sched_id = CL ? blockIdx.x / 2 : blockIdx.x; // cluster (or CTA) index
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzled activation slabs
     uint8_t *smem = reinterpret_cast<uint8_t *>(
@@ -255,17 +283,21 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
     Sched sched;
     sched.k_tiles = args.k / kTileK;
     sched.n_tiles = (args.n + kTileN - 1) / kTileN;
+    if (CL) sched.n_tiles /= 2; // unit space counts n-tile PAIRS (launcher ensures even)
     sched.m_tiles = (args.m + NTOK - 1) / NTOK;
     sched.total_units = sched.k_tiles * sched.n_tiles * sched.m_tiles;
-    sched.grid = gridDim.x;
-    const uint32_t u_begin = sched.begin(blockIdx.x);
-    const uint32_t u_end = sched.begin(blockIdx.x + 1);
+    sched.grid = CL ? gridDim.x / 2 : gridDim.x;
+    sched.n_mul = CL ? 2 : 1;
+    sched.n_add = cta_rank;
+    const uint32_t u_begin = sched.begin(sched_id);
+    const uint32_t u_end = sched.begin(sched_id + 1);
 
     if (warp == kProducerWarp && lane == 0) {
         prefetch_tensormap(&tmap_act);
         for (int i = 0; i < C::kStages; ++i) {
             mbar_init(&bars->full[i], 1);
-            mbar_init(&bars->empty[i], C::kStageWarps + 1);
+            mbar_init(&bars->empty[i], C::kStageWarps);
+            mbar_init(&bars->empty_act[i], CL ? 2 : 1);
         }
         for (int i = 0; i < C::kAStages; ++i) {
             mbar_init(&bars->a_full[i], C::kStageWarps);
@@ -281,14 +313,17 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
     tc_fence_before();
     // The producer warp initialised the barriers itself, so it only signals the setup
     // barrier and starts streaming weights while the others wait for the TMEM base.
-    if (warp == kProducerWarp) {
+    if (CL) {
+        // remote barriers must exist before the peer multicasts into them
+        cluster_sync();
+    } else if (warp == kProducerWarp) {
         __syncwarp();
         asm volatile("bar.arrive %0, %1;" ::"n"(kSetupBarId), "n"(kNumThreads) : "memory");
     } else {
         named_bar_sync(kSetupBarId, kNumThreads);
     }
     tc_fence_after();
-    const uint32_t tmem = warp == kProducerWarp ? 0u : bars->tmem_base;
+    const uint32_t tmem = (!CL && warp == kProducerWarp) ? 0u : bars->tmem_base;
     const uint32_t tmem_a0 = tmem + C::kAccCols;
     if (threadIdx.x == 0) trace_stamp(args, 1);
 
@@ -336,7 +371,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                     if (it >= it_lo) {
                         const uint32_t s = it % C::kStages;
                         const uint32_t ph = (it / C::kStages) & 1;
-                        if (pass == 2) mbar_wait(&bars->empty[s], ph ^ 1);
+                        if (pass == 2) {
+                            mbar_wait(&bars->empty[s], ph ^ 1);
+                            mbar_wait(&bars->empty_act[s], ph ^ 1);
+                        }
                         if (elect_one()) {
                             uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
                             trace_stage(args, it, do_w ? 0 : 1);
@@ -361,7 +399,17 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                                                      smem_u32(&bars->full[s])),
                                                  "r"((uint32_t)C::kActBytes)
                                                  : "memory");
-                                else
+                                else if (CL) {
+                                    // my half of the token rows, one 128-byte-row slab per
+                                    // call, delivered to both CTAs of the cluster
+#pragma unroll
+                                    for (int sl = 0; sl < C::kSubs; ++sl)
+                                        tma_load_3d_mc(st + sl * (NTOK * 128) +
+                                                           cta_rank * (NTOK / 2) * 128,
+                                                       &tmap_act, &bars->full[s], 0,
+                                                       g.m_tile * NTOK + cta_rank * (NTOK / 2),
+                                                       k_slab + sl, (uint16_t)3);
+                                } else
                                     tma_load_3d(st, &tmap_act, &bars->full[s], 0, g.m_tile * NTOK,
                                                 k_slab);
                             }
@@ -410,7 +458,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                                    idesc, (i != 0 || j >= C::kChains) ? 1u : 0u);
                     }
                     tc_commit(&bars->a_empty[ta]);
-                    tc_commit(&bars->empty[s]);
+                    if (CL)
+                        tc_commit_mc(&bars->empty_act[s], (uint16_t)3);
+                    else
+                        tc_commit(&bars->empty_act[s]);
                     if (i + 1 == n_stage) tc_commit(&bars->acc_full[acc]);
                     trace_stage(args, it, 6);
                 }
@@ -547,8 +598,11 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             const bool is_reducer = !full_k && g.kt0 == 0;
             const bool is_contrib = !full_k && g.kt0 != 0;
             float *slot = args.ws_partials + (size_t)blockIdx.x * (kTileN * NTOK);
-            uint32_t b_first = blockIdx.x, b_last = blockIdx.x;
+            // ids below are scheduling units (clusters if CL); the contributor of unit b to
+            // THIS CTA's tile is the CTA of the same cluster rank, i.e. slot b * n_mul + n_add
+            uint32_t b_first = sched_id, b_last = sched_id;
             if (is_reducer) b_last = sched.owner(g.tile * sched.k_tiles + sched.k_tiles - 1);
+            const uint32_t out_tile = g.n_tile * sched.m_tiles + g.m_tile;
 
             // Reducer: the other contributors published long ago, so their partials
             // for the first 16 tokens are summed (in CTA order) into registers while
@@ -564,14 +618,15 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                     do {
                         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
                                      : "=r"(seen)
-                                     : "l"(args.ws_counters + g.tile)
+                                     : "l"(args.ws_counters + out_tile)
                                      : "memory");
                     } while (seen < need);
                 }
                 named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
 #pragma unroll 1
                 for (uint32_t b = b_first + 1; b <= b_last; ++b) {
-                    const float *p = args.ws_partials + (size_t)b * (kTileN * NTOK) + row;
+                    const float *p = args.ws_partials +
+                                     (size_t)(b * sched.n_mul + sched.n_add) * (kTileN * NTOK) + row;
                     float x[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
@@ -622,9 +677,11 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
 #pragma unroll
                         for (int sg = 0; sg < kSeg; ++sg) {
                             const bool seg_ok = bb + sg <= b_last;
-                            const float *p = args.ws_partials +
-                                             (size_t)(seg_ok ? bb + sg : b_last) * (kTileN * NTOK) +
-                                             (size_t)c0 * kTileN + row;
+                            const float *p =
+                                args.ws_partials +
+                                (size_t)((seg_ok ? bb + sg : b_last) * sched.n_mul + sched.n_add) *
+                                    (kTileN * NTOK) +
+                                (size_t)c0 * kTileN + row;
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
                                 x[sg][j] = (seg_ok && (uint32_t)(c0 + j) < m_valid)
@@ -657,11 +714,11 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                 named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
                 if (ew_tid == 0)
                     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(
-                                     args.ws_counters + g.tile)
+                                     args.ws_counters + out_tile)
                                  : "memory");
             } else if (is_reducer) {
                 named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
-                if (ew_tid == 0) args.ws_counters[g.tile] = 0; // self-cleaning
+                if (ew_tid == 0) args.ws_counters[out_tile] = 0; // self-cleaning
             }
             u += g.kt1 - g.kt0;
         }
@@ -669,7 +726,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
 
     if (threadIdx.x == kFirstEpilogueWarp * 32) trace_stamp(args, 7);
     tc_fence_before();
-    __syncthreads();
+    if (CL)
+        cluster_sync(); // the peer may still multicast into / arrive on this CTA's smem
+    else
+        __syncthreads();
     if (threadIdx.x == 0) trace_stamp(args, 8);
     if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
 }
@@ -695,7 +755,7 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int MODE, int NTOK, int KS>
+template <int MODE, int NTOK, int KS, bool CL = false>
 int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     using C = Cfg<MODE, NTOK, KS>;
     EncodeTiledFn encode = get_encode_fn();
@@ -705,7 +765,7 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     CUtensorMap tmap;
     const cuuint64_t dims[3] = {64, args.m, args.k / 64};
     const cuuint64_t strides[2] = {(cuuint64_t)args.k * 2, 128};
-    const cuuint32_t box[3] = {64, (cuuint32_t)NTOK, (cuuint32_t)C::kSubs};
+    const cuuint32_t box[3] = {64, (cuuint32_t)(CL ? NTOK / 2 : NTOK), (cuuint32_t)(CL ? 1 : C::kSubs)};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&tmap,
                         C::kIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
@@ -716,7 +776,7 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return kLaunchCudaError;
 
     static bool attr_set[64] = {}; // per instantiation, per device
-    auto kern = fp4_gemm_kernel<MODE, NTOK, KS>;
+    auto kern = fp4_gemm_kernel<MODE, NTOK, KS, CL>;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return kLaunchCudaError;
     if (!attr_set[dev & 63]) {
@@ -727,8 +787,12 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     }
     const uint64_t n_tiles = (args.n + kTileN - 1) / kTileN;
     const uint64_t m_tiles = (args.m + NTOK - 1) / NTOK;
-    const uint64_t units = n_tiles * m_tiles * (args.k / kTileK);
-    const unsigned grid = (unsigned)(units < (uint64_t)num_sms ? units : (uint64_t)num_sms);
+    const uint64_t units = (CL ? n_tiles / 2 : n_tiles) * m_tiles * (args.k / kTileK);
+    unsigned grid = (unsigned)(units < (uint64_t)num_sms ? units : (uint64_t)num_sms);
+    if (CL) {
+        const uint64_t clusters = units < (uint64_t)(num_sms / 2) ? units : (uint64_t)(num_sms / 2);
+        grid = (unsigned)clusters * 2;
+    }
     if (m_tiles * n_tiles > kMaxTiles || grid > kMaxGrid || units >= (1ull << 31))
         return kLaunchBadShape;
     cudaLaunchConfig_t cfg = {};
@@ -736,23 +800,35 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     cfg.blockDim = dim3(kNumThreads);
     cfg.dynamicSmemBytes = C::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = args.use_pdl ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = CL ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap, args);
     return e == cudaSuccess ? kLaunchOk : kLaunchCudaError;
 }
 
 template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
                                     cudaStream_t stream) {
+    // 2-CTA multicast clusters need an even number of n-tiles (pairs) and enough tokens
+    // for the shared tile to matter
+    const uint32_t n_tiles = (args.n + kTileN - 1) / kTileN;
+    const bool cluster_ok = args.use_cluster && n_tiles % 2 == 0 && args.n % kTileN == 0;
     switch (ntok) {
     case 16: return launch_variant<MODE, 16, 256>(args, num_sms, stream);
     case 32: return launch_variant<MODE, 32, 256>(args, num_sms, stream);
     case 64: return launch_variant<MODE, 64, 256>(args, num_sms, stream);
-    case 128: return launch_variant<MODE, 128, 128>(args, num_sms, stream);
-    case 256: return launch_variant<MODE, 256, 64>(args, num_sms, stream);
+    case 128:
+        return cluster_ok ? launch_variant<MODE, 128, 128, true>(args, num_sms, stream)
+                          : launch_variant<MODE, 128, 128>(args, num_sms, stream);
+    case 256:
+        return cluster_ok ? launch_variant<MODE, 256, 64, true>(args, num_sms, stream)
+                          : launch_variant<MODE, 256, 64>(args, num_sms, stream);
     default: return kLaunchNoKernel;
     }
 }

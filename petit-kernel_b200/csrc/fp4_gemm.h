@@ -25,6 +25,7 @@ struct GemmArgs {
     uint32_t two29;         // 1u << 29, passed at run time (see dequant.cuh)
     unsigned long long add64; // 0x70007000ull << 32, same reason
     uint32_t debug_flags;   // experiments only (PETIT_DEBUG_FLAGS); 0 in production
+    uint32_t use_cluster;   // allow the 2-CTA multicast variant for 128/256-token tiles
     uint32_t use_pdl;       // launch with programmatic stream serialisation
     uint32_t skew_cycles;   // initial phase skew between k-slice warps (tuning knob)
     unsigned long long *trace; // optional [grid][16] globaltimer stamps (debug), else null

@@ -160,6 +160,7 @@ static void run_case(bool mx, bool bf16, unsigned m, unsigned n, unsigned k, int
 }
 
 int main(int argc, char **argv) {
+    setvbuf(stdout, nullptr, _IOLBF, 0); // progress survives a timeout kill
     bool full = argc > 1 && !strcmp(argv[1], "full");
     // reference python cases (tests/ops/test_fp4_gemm_quark.py:27-35)
     run_case(false, true, 64, 128, 256, 0, 1.37f, true);

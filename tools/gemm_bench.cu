@@ -167,6 +167,48 @@ int main(int argc, char **argv) {
                 }
                 cudaFree(d_tr);
             }
+            if (getenv("PETIT_TRACE2")) {
+                // two consecutive launches stamped into separate buffers on the common
+                // globaltimer base: shows how launch i+1 overlaps the tail of launch i
+                const size_t words = 160 * 16 + 64 * 8;
+                unsigned long long *d_tr[2];
+                for (int j = 0; j < 2; ++j) {
+                    CK(cudaMalloc(&d_tr[j], words * 8));
+                    CK(cudaMemset(d_tr[j], 0, words * 8));
+                }
+                call(0);
+                call(1);
+                petit_debug_set_trace(d_tr[0]);
+                call(2);
+                petit_debug_set_trace(d_tr[1]);
+                call(3);
+                petit_debug_set_trace(nullptr);
+                call(4);
+                CK(cudaDeviceSynchronize());
+                std::vector<unsigned long long> tr[2];
+                unsigned long long t0 = ~0ull;
+                for (int j = 0; j < 2; ++j) {
+                    tr[j].resize(words);
+                    CK(cudaMemcpy(tr[j].data(), d_tr[j], words * 8, cudaMemcpyDeviceToHost));
+                }
+                for (int b = 0; b < 160; ++b) if (tr[0][b * 16]) t0 = std::min(t0, tr[0][b * 16]);
+                const char *names[9] = {"entry", "setup_done", "griddep_wait_done", "first_stage_landed",
+                                        "dequant_done", "mma_issued_all", "last_acc_full", "epilogue_done", "exit"};
+                for (int j = 0; j < 2; ++j) {
+                    printf("  launch %d (us since launch-0 first entry): event min/avg/max\n", j);
+                    for (int e = 0; e < 9; ++e) {
+                        double mn = 1e30, mx2 = 0, sum = 0; int cnt = 0;
+                        for (int b = 0; b < 160; ++b) {
+                            unsigned long long v = tr[j][b * 16 + e];
+                            if (!v || !tr[j][b * 16]) continue;
+                            double d = (double)((long long)(v - t0)) * 1e-3;
+                            mn = std::min(mn, d); mx2 = std::max(mx2, d); sum += d; ++cnt;
+                        }
+                        if (cnt) printf("    %-20s %7.2f %7.2f %7.2f\n", names[e], mn, sum / cnt, mx2);
+                    }
+                    cudaFree(d_tr[j]);
+                }
+            }
             double bytes = (double)wbytes + sbytes + 2.0 * m * s.k + 2.0 * m * s.n + 4;
             double flops = 2.0 * m * s.n * s.k;
             printf("%-7s %s %s M=%-5u  %9.2f us  %7.0f GB/s (%5.1f%% of %.0f)  %7.1f TFLOPS (%5.1f%% of %.0f)\n",

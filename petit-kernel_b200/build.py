@@ -52,7 +52,9 @@ def build_lib(force: bool = False) -> str:
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
         if force or _newer(obj, [os.path.join(CSRC, src)] + hs):
-            _run([NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+            # PETIT_EXTRA_NVCC_FLAGS: e.g. -DPETIT_DEBUG_HOOKS for the experiment switches
+            _run([NVCC, *ARCH, *os.environ.get("PETIT_EXTRA_NVCC_FLAGS", "").split(),
+                  "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
                   "-Xptxas", "-v" if os.environ.get("PETIT_BUILD_VERBOSE") else "-O3",
                   "-I", os.path.join(ROOT, "include"), "-I", CSRC,
                   "-c", os.path.join(CSRC, src), "-o", obj])

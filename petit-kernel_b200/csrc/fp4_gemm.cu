@@ -83,9 +83,11 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     static constexpr int kStageBytes =
         (kActBytes + kWBytes + kScBytes + 1023) / 1024 * 1024;
     static constexpr int kBarrierBytes = 1024;
-    static constexpr int kStages = (kSmemBudget - kBarrierBytes - 1024) / kStageBytes > 16
-                                       ? 16
-                                       : (kSmemBudget - kBarrierBytes - 1024) / kStageBytes;
+    // epilogue staging: two [16 tokens][128 rows] 16-bit tiles feeding TMA stores
+    static constexpr int kOutStageBytes = 16 * 128 * 2;
+    static constexpr int kOutBytes = 2 * kOutStageBytes;
+    static constexpr int kRingBudget = kSmemBudget - kBarrierBytes - kOutBytes - 1024;
+    static constexpr int kStages = kRingBudget / kStageBytes > 16 ? 16 : kRingBudget / kStageBytes;
     // Small-N MMAs that accumulate into the same TMEM columns serialise on the
     // full MMA latency (~130 clk measured), so consecutive k-steps rotate over
     // kChains independent accumulators that the epilogue sums.
@@ -115,7 +117,7 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     static constexpr int kACols = KS / 2;          // TMEM columns of one A stage
     static constexpr int kAStagesRaw = (512 - kAccCols) / kACols;
     static constexpr int kAStages = kAStagesRaw > 8 ? 8 : kAStagesRaw;
-    static constexpr int kSmemBytes = kBarrierBytes + kStages * kStageBytes + 1024;
+    static constexpr int kSmemBytes = kBarrierBytes + kOutBytes + kStages * kStageBytes + 1024;
     static_assert(kStages >= 2, "need at least two smem stages");
     static_assert(kAStages >= 2, "need at least two TMEM A stages");
 };
@@ -128,6 +130,7 @@ struct Barriers {
     uint64_t a_empty[8];
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
+    uint64_t part_full;     // reducer: partial tiles landed in the (drained) stage ring
     uint32_t tmem_base;
     uint32_t flag;
 };
@@ -245,12 +248,9 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return v;
 }
-template <bool kBf16>
-__device__ __forceinline__ void store_out(void *c, size_t off, float r) {
-    if (kBf16)
-        reinterpret_cast<__nv_bfloat16 *>(c)[off] = __float2bfloat16_rn(r);
-    else
-        reinterpret_cast<__half *>(c)[off] = __float2half_rn(r);
+template <bool kBf16> __device__ __forceinline__ uint16_t to_bits16(float r) {
+    if (kBf16) return __bfloat16_as_ushort(__float2bfloat16_rn(r));
+    return __half_as_ushort(__float2half_rn(r));
 }
 
 // ---------------------------------------------------------------------------
@@ -262,7 +262,8 @@ __device__ __forceinline__ void store_out(void *c, size_t off, float r) {
 // traffic that bounds the prefill kernel (measured 42.7 B/clk/SM, the L2 fabric cap).
 template <int MODE, int NTOK, int KS, bool CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
-fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
+fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
+                const __grid_constant__ CUtensorMap tmap_out, GemmArgs args) {
     using C = Cfg<MODE, NTOK, KS>;
     uint32_t cta_rank = 0;
     if (CL) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -272,7 +273,8 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
     uint8_t *smem = reinterpret_cast<uint8_t *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     Barriers *bars = reinterpret_cast<Barriers *>(smem);
-    uint8_t *stage_base = smem + C::kBarrierBytes;
+    uint8_t *out_stage = smem + C::kBarrierBytes;
+    uint8_t *stage_base = out_stage + C::kOutBytes;
 
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     if (threadIdx.x == 0) trace_stamp(args, 0);
@@ -294,6 +296,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
 
     if (warp == kProducerWarp && lane == 0) {
         prefetch_tensormap(&tmap_act);
+        prefetch_tensormap(&tmap_out);
         for (int i = 0; i < C::kStages; ++i) {
             mbar_init(&bars->full[i], 1);
             mbar_init(&bars->empty[i], C::kStageWarps);
@@ -307,6 +310,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             mbar_init(&bars->acc_full[i], 1);
             mbar_init(&bars->acc_empty[i], kNumEpilogueWarps);
         }
+        mbar_init(&bars->part_full, 1);
         fence_mbar_init();
     }
     if (warp == kMmaWarp) tmem_alloc(&bars->tmem_base, 512);
@@ -578,13 +582,13 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
         float gs = *args.global_scale;
         gs *= epilogue_factor<MODE>(); // power of two folded out of the A operand
         uint32_t seg = 0;
+        uint32_t out_groups = 0; // 16-token groups stored so far (staging buffer parity)
         for (uint32_t u = u_begin; u < u_end; ++seg) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t rows = tile_rows(args.n, g.n_tile);
             const uint32_t acc = seg % C::kNumAcc;
             const uint32_t acc_ph = (seg / C::kNumAcc) & 1;
             const bool full_k = g.kt0 == 0 && g.kt1 == sched.k_tiles;
-            const uint32_t n_idx = g.n_tile * kTileN + row;
             const uint32_t m0 = g.m_tile * NTOK;
             const uint32_t m_valid = args.m - m0 < (uint32_t)NTOK ? args.m - m0 : NTOK;
             const bool row_ok = row < rows;
@@ -611,6 +615,8 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
             float pre[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) pre[j] = 0.f;
+            const bool last_seg = u + (g.kt1 - g.kt0) >= u_end;
+            if (ew_tid == 0 && last_seg) trace_stamp(args, 11);
             if (is_reducer) {
                 if (ew_tid == 0) {
                     const uint32_t need = b_last - b_first;
@@ -621,6 +627,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                                      : "l"(args.ws_counters + out_tile)
                                      : "memory");
                     } while (seen < need);
+                    if (last_seg) trace_stamp(args, 12);
                 }
                 named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
 #pragma unroll 1
@@ -635,9 +642,29 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                     for (int j = 0; j < 16; ++j) pre[j] += x[j];
                 }
             }
+            if (ew_tid == 0 && last_seg) trace_stamp(args, 13);
             while (!mbar_try_wait(&bars->acc_full[acc], acc_ph)) __nanosleep(32);
             tc_fence_after();
-            if (ew_tid == 0 && u + (g.kt1 - g.kt0) >= u_end) trace_stamp(args, 6);
+            if (ew_tid == 0 && last_seg) trace_stamp(args, 6);
+            // Reducer, tokens 16.. : the reducer segment is the LAST of this CTA's range and
+            // its MMAs are complete, so the whole stage ring is idle -- the contributors'
+            // partial tiles (tokens 16..m_valid) are pulled into it with one bulk copy each
+            // (one L2 round trip in total instead of one per 16-token group).
+            constexpr uint32_t kRingFit = (uint32_t)(C::kStages * C::kStageBytes) / (NTOK * kTileN * 4);
+            const uint32_t n_ring = (is_reducer && m_valid > 16u)
+                                        ? (b_last - b_first < kRingFit ? b_last - b_first : kRingFit)
+                                        : 0u;
+            if (n_ring && ew_tid == 0) {
+                const uint32_t bytes = (m_valid - 16u) * (kTileN * 4);
+                mbar_arrive_expect_tx(&bars->part_full, n_ring * bytes);
+                for (uint32_t i = 0; i < n_ring; ++i)
+                    bulk_g2s(stage_base + (size_t)i * (NTOK * kTileN * 4) + 16 * kTileN * 4,
+                             args.ws_partials +
+                                 (size_t)((b_first + 1 + i) * sched.n_mul + sched.n_add) *
+                                     (kTileN * NTOK) +
+                                 16 * kTileN,
+                             bytes, &bars->part_full);
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < NTOK; c0 += 16) {
                 if ((uint32_t)c0 >= m_valid) break; // tokens beyond M are never stored
@@ -649,6 +676,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
                 }
+                if (ew_tid == 0 && last_seg && c0 == 0) trace_stamp(args, 14);
 #pragma unroll
                 for (int ch = 1; ch < C::kChains; ++ch) {
                     uint32_t r1[16];
@@ -657,6 +685,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
                 }
+                if (ew_tid == 0 && last_seg && c0 == 0) trace_stamp(args, 9);
                 if (is_contrib) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
@@ -667,42 +696,57 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
                 if (is_reducer && c0 == 0) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += pre[j];
-                } else if (is_reducer && row_ok) {
-                    // all loads of a pass are issued before the first add: one L2
-                    // round trip per pass of up to kSeg partials
-                    constexpr int kSeg = 3;
+                } else if (is_reducer && !PETIT_DBG(args.debug_flags, 32u)) {
+                    if (n_ring) {
+                        if (c0 == 16) {
+                            while (!mbar_try_wait(&bars->part_full, 0)) __nanosleep(32);
+                        }
 #pragma unroll 1
-                    for (uint32_t bb = b_first + 1; bb <= b_last; bb += kSeg) {
-                        float x[kSeg][16];
-#pragma unroll
-                        for (int sg = 0; sg < kSeg; ++sg) {
-                            const bool seg_ok = bb + sg <= b_last;
-                            const float *p =
-                                args.ws_partials +
-                                (size_t)((seg_ok ? bb + sg : b_last) * sched.n_mul + sched.n_add) *
-                                    (kTileN * NTOK) +
-                                (size_t)c0 * kTileN + row;
+                        for (uint32_t i = 0; i < n_ring; ++i) {
+                            const uint32_t src = smem_u32(stage_base) + i * (NTOK * kTileN * 4) +
+                                                 (uint32_t)c0 * (kTileN * 4) + row * 4;
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                x[sg][j] = (seg_ok && (uint32_t)(c0 + j) < m_valid)
-                                               ? __ldcg(p + (size_t)j * kTileN)
-                                               : 0.f;
+                                if ((uint32_t)(c0 + j) < m_valid)
+                                    v[j] += __uint_as_float(lds_u32(src + j * (kTileN * 4)));
                         }
+                    }
+                    // partial tiles that did not fit the ring (tile split over many CTAs):
+                    // straight from L2, in CTA order like the rest
+#pragma unroll 1
+                    for (uint32_t bb = b_first + 1 + n_ring; bb <= b_last; ++bb) {
+                        const float *p = args.ws_partials +
+                                         (size_t)(bb * sched.n_mul + sched.n_add) * (kTileN * NTOK) +
+                                         (size_t)c0 * kTileN + row;
+                        float x[16];
 #pragma unroll
-                        for (int sg = 0; sg < kSeg; ++sg)
+                        for (int j = 0; j < 16; ++j)
+                            x[j] = (uint32_t)(c0 + j) < m_valid ? __ldcg(p + (size_t)j * kTileN) : 0.f;
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] += x[sg][j];
+                        for (int j = 0; j < 16; ++j) v[j] += x[j];
                     }
                 }
-                if (row_ok) {
+                if (!PETIT_DBG(args.debug_flags, 64u)) {
+                    // [16 tokens][128 rows] 16-bit staging tile -> one TMA store; the tensor
+                    // map clips tokens >= M and rows >= N.  Buffer (out_groups & 1) was
+                    // released at the previous group's barrier (see the wait below).
+                    uint16_t *stg = reinterpret_cast<uint16_t *>(
+                        out_stage + (out_groups & 1) * C::kOutStageBytes);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const uint32_t t = c0 + j;
-                        if (t < m_valid)
-                            store_out<C::kIsBf16>(args.c, (size_t)(m0 + t) * args.n + n_idx,
-                                                  v[j] * gs);
+                    for (int j = 0; j < 16; ++j) stg[j * kTileN + row] = to_bits16<C::kIsBf16>(v[j] * gs);
+                    fence_proxy_async();
+                    if (ew_tid == 0 && last_seg && c0 == 0) trace_stamp(args, 10);
+                    // the store of the previous group must have finished reading the
+                    // other buffer before anyone refills it after this barrier
+                    if (ew_tid == 0) bulk_wait_group_read<0>();
+                    named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
+                    if (ew_tid == 0) {
+                        tma_store_2d(&tmap_out, stg, (int)(g.n_tile * kTileN), (int)(m0 + c0));
+                        bulk_commit_group();
                     }
+                    ++out_groups;
                 }
+                if (ew_tid == 0 && last_seg && c0 == 0) trace_stamp(args, 15);
             }
             // accumulator drained -> MMA may reuse it
             tc_fence_before();
@@ -724,7 +768,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, GemmArgs args) {
         }
     }
 
-    if (threadIdx.x == kFirstEpilogueWarp * 32) trace_stamp(args, 7);
+    if (threadIdx.x == kFirstEpilogueWarp * 32) {
+        bulk_wait_group_read<0>(); // staging smem must outlive the last TMA store's read
+        trace_stamp(args, 7);
+    }
     tc_fence_before();
     if (CL)
         cluster_sync(); // the peer may still multicast into / arrive on this CTA's smem
@@ -774,6 +821,15 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return kLaunchCudaError;
+    // output [M, N] 16-bit row-major; the epilogue stores [16 tokens][128 rows] boxes
+    CUtensorMap tmap_out;
+    const cuuint64_t odims[2] = {args.n, args.m};
+    const cuuint64_t ostrides[1] = {(cuuint64_t)args.n * 2};
+    const cuuint32_t obox[2] = {kTileN, 16};
+    r = encode(&tmap_out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, args.c, odims, ostrides, obox, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return kLaunchCudaError;
 
     static bool attr_set[64] = {}; // per instantiation, per device
     auto kern = fp4_gemm_kernel<MODE, NTOK, KS, CL>;
@@ -809,7 +865,7 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CL ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap, args);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_out, args);
     return e == cudaSuccess ? kLaunchOk : kLaunchCudaError;
 }
 

@@ -23,6 +23,9 @@
  *     never checks the launch, gemm.h:135-145).
  *   - the packed layouts are Blackwell tile layouts; they are
  *     opaque to callers exactly as the reference's are.
+ *   - the GEMM moves every operand with TMA: the activation, output, packed weight
+ *     and packed scale base addresses must be 16-byte aligned (else
+ *     PETIT_ERROR_PROBLEM_SHAPE); rows need no padding.
  *
  * Semantics kept from the reference:
  *   - return 0 on success, PETIT_ERROR_PROBLEM_SHAPE (1), PETIT_ERROR_KERNEL_SHAPE (2)

@@ -61,11 +61,13 @@ bool decode_solution(uint64_t id, Decoded *d) {
 }
 
 // Default solution (the role of ChooseDefaultFp4Fp16Solution, algo_chooser.cc:64-132):
-// the smallest token tile that holds M up to 128 tokens; beyond that 256-token tiles
-// only once there are enough of them (>= 8 per SM) to amortise their longer
-// prologue/epilogue -- measured on the 70B shapes (gpurun_out bench27: qkv M=1024
-// 58 % of peak with 128-token tiles vs 49 % with 256; gate_up 70 % vs 68 %).
-int default_ntok(unsigned m, unsigned n) {
+// the smallest token tile that holds M up to 128 tokens.  Beyond that, 256-token tiles
+// run the main loop ~17 % faster than 128-token tiles (measured, Llama-70B shapes,
+// M = 512..4096: 82-89 % vs 70-75 % of the bf16 peak) but pay a longer final epilogue
+// and pad M to a multiple of 256, so they are chosen when the padded work still comes
+// out ahead and every SM has enough 256-token units (>= 40) to amortise the tail
+// (o_proj M=512 = 28 units/SM: 58 % with 256 vs 63 % with 128; qkv M=512 = 35: tie).
+int default_ntok(unsigned m, unsigned n, unsigned k) {
     if (const char *e = std::getenv("PETIT_FORCE_NTOK")) {
         int v = std::atoi(e);
         for (int t : kTokVariants)
@@ -73,9 +75,12 @@ int default_ntok(unsigned m, unsigned n) {
     }
     for (int t : kTokVariants)
         if (t <= 128 && m <= (unsigned)t) return t;
-    const unsigned long long tiles256 =
-        (unsigned long long)((n + layout::kTileN - 1) / layout::kTileN) * ((m + 255) / 256);
-    return tiles256 >= 8ull * 148 ? 256 : 128;
+    const unsigned long long n_tiles = (n + layout::kTileN - 1) / layout::kTileN;
+    const unsigned long long k_tiles = k / layout::kTileK;
+    const unsigned long long pad256 = (m + 255ull) / 256 * 256, pad128 = (m + 127ull) / 128 * 128;
+    const unsigned long long units256 = n_tiles * (pad256 / 256) * k_tiles;
+    const bool faster = pad256 * 85 <= pad128 * 100;
+    return faster && units256 >= 40ull * 148 ? 256 : 128;
 }
 
 bool problem_shape_ok(unsigned n, unsigned k) {
@@ -149,7 +154,7 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
         if (!problem_shape_ok(n, k)) return PETIT_ERROR_PROBLEM_SHAPE;
         if (hints->a_type != PETIT_DTYPE_FP16 && hints->a_type != PETIT_DTYPE_BF16)
             return PETIT_ERROR_PROBLEM_SHAPE;
-        d.ntok = default_ntok(m, n);
+        d.ntok = default_ntok(m, n, k);
         d.elem_b = is_mx ? kElemMx : kElemNv;
         d.mfma = hints->a_type == PETIT_DTYPE_BF16 ? kMfmaBf16 : kMfmaF16;
     } else {
@@ -168,6 +173,13 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
         return PETIT_ERROR_KERNEL_SHAPE;
     if (!problem_shape_ok(n, k)) return PETIT_ERROR_PROBLEM_SHAPE; // ConfigSelector::Invoke
 
+    // TMA moves the activations in, the output out and the packed weights / scales
+    // by bulk copy: all four base addresses must be 16-byte aligned (torch allocations
+    // are; a view that starts at an odd element is not).
+    if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(c) |
+          reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(scales)) & 15) != 0)
+        return PETIT_ERROR_PROBLEM_SHAPE;
+
     Workspace ws;
     int num_sms = 0;
     int err = get_context(stream, &ws, &num_sms);
@@ -184,8 +196,6 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
     args.m = m;
     args.n = n;
     args.k = k;
-    args.two29 = 1u << 29;
-    args.add64 = 0x70007000ull << 32;
     args.trace = g_trace;
     {
         static const int pdl = [] {

@@ -83,9 +83,10 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     static constexpr int kStageBytes =
         (kActBytes + kWBytes + kScBytes + 1023) / 1024 * 1024;
     static constexpr int kBarrierBytes = 1024;
-    // epilogue staging: two [16 tokens][128 rows] 16-bit tiles feeding TMA stores
+    // epilogue staging: three [16 tokens][128 rows] 16-bit tiles feeding TMA stores
     static constexpr int kOutStageBytes = 16 * 128 * 2;
-    static constexpr int kOutBytes = 2 * kOutStageBytes;
+    static constexpr int kOutBufs = 3;
+    static constexpr int kOutBytes = kOutBufs * kOutStageBytes;
     static constexpr int kRingBudget = kSmemBudget - kBarrierBytes - kOutBytes - 1024;
     static constexpr int kStages = kRingBudget / kStageBytes > 16 ? 16 : kRingBudget / kStageBytes;
     // Small-N MMAs that accumulate into the same TMEM columns serialise on the
@@ -582,7 +583,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         float gs = *args.global_scale;
         gs *= epilogue_factor<MODE>(); // power of two folded out of the A operand
         uint32_t seg = 0;
-        uint32_t out_groups = 0; // 16-token groups stored so far (staging buffer parity)
+        uint32_t out_buf = 0; // staging buffer the next 16-token group goes to
         for (uint32_t u = u_begin; u < u_end; ++seg) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t rows = tile_rows(args.n, g.n_tile);
@@ -728,23 +729,21 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 }
                 if (!PETIT_DBG(args.debug_flags, 64u)) {
                     // [16 tokens][128 rows] 16-bit staging tile -> one TMA store; the tensor
-                    // map clips tokens >= M and rows >= N.  Buffer (out_groups & 1) was
-                    // released at the previous group's barrier (see the wait below).
-                    uint16_t *stg = reinterpret_cast<uint16_t *>(
-                        out_stage + (out_groups & 1) * C::kOutStageBytes);
+                    // map clips tokens >= M and rows >= N.  Three buffers in rotation: the
+                    // wait below (before the barrier) leaves only the previous group's store
+                    // in flight, so the buffer the NEXT group fills is known to be drained.
+                    uint16_t *stg = reinterpret_cast<uint16_t *>(out_stage + out_buf * C::kOutStageBytes);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) stg[j * kTileN + row] = to_bits16<C::kIsBf16>(v[j] * gs);
                     fence_proxy_async();
                     if (ew_tid == 0 && last_seg && c0 == 0) trace_stamp(args, 10);
-                    // the store of the previous group must have finished reading the
-                    // other buffer before anyone refills it after this barrier
-                    if (ew_tid == 0) bulk_wait_group_read<0>();
+                    if (ew_tid == 0) bulk_wait_group_read<1>();
                     named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
                     if (ew_tid == 0) {
                         tma_store_2d(&tmap_out, stg, (int)(g.n_tile * kTileN), (int)(m0 + c0));
                         bulk_commit_group();
                     }
-                    ++out_groups;
+                    out_buf = out_buf == C::kOutBufs - 1 ? 0 : out_buf + 1;
                 }
                 if (ew_tid == 0 && last_seg && c0 == 0) trace_stamp(args, 15);
             }

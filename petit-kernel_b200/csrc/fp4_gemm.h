@@ -22,8 +22,6 @@ struct GemmArgs {
     float *ws_partials;     // stream-K partial tiles
     unsigned *ws_counters;  // per-tile arrival counters (zero between launches)
     uint32_t m, n, k;
-    uint32_t two29;         // 1u << 29, passed at run time (see dequant.cuh)
-    unsigned long long add64; // 0x70007000ull << 32, same reason
     uint32_t debug_flags;   // experiments only (PETIT_DEBUG_FLAGS); 0 in production
     uint32_t use_cluster;   // allow the 2-CTA multicast variant for 128/256-token tiles
     uint32_t use_pdl;       // launch with programmatic stream serialisation

@@ -346,6 +346,45 @@ def test_out_variant_writes_in_place(pk):
         pk.ops.mul_nvfp4_a16_out(out[:, :256], ac, b, sp, gsc, m, n, k, -1)
 
 
+def test_unaligned_operands_are_rejected(pk):
+    """TMA needs 16-byte aligned bases: a view starting at an odd element must fail
+    loudly (PETIT_ERROR_PROBLEM_SHAPE), never compute on the wrong bytes."""
+    m, n, k = 16, 512, 1024
+    a, q, s, gs = orc.make_nvfp4_case(m, n, k, 10)
+    b, sp = pack_nvfp4(pk, q, s, n, k)
+    gsc = gs.cuda()
+    flat = torch.zeros(m * k + 8, dtype=torch.bfloat16, device="cuda")
+    a_off = flat[1 : 1 + m * k].view(m, k)
+    a_off.copy_(a.cuda())
+    assert a_off.data_ptr() % 16 != 0
+    with pytest.raises(RuntimeError):
+        pk.mul_nvfp4_a16(a_off, b, sp, gsc, m, n, k, -1)
+    # the same values from an aligned buffer are fine
+    ref = pk.mul_nvfp4_a16(a_off.clone(), b, sp, gsc, m, n, k, -1)
+    assert torch.isfinite(ref.float()).all()
+
+
+@pytest.mark.parametrize("m,n,k", [(1024, 2048, 2048), (700, 4096, 1024), (2048, 1024, 4096)])
+def test_prefill_tiles_and_cluster_variant(pk, m, n, k):
+    """128/256-token tiles (with and without the 2-CTA multicast cluster variant, chosen by
+    the default rule or forced through explicit solution ids) against the oracle GEMM."""
+    a, q, s, gs = orc.make_nvfp4_case(m, n, k, 11)
+    b, sp = pack_nvfp4(pk, q, s, n, k)
+    ac, gsc = a.cuda(), gs.cuda()
+    want = orc.nvfp4_gemm_ref_torch(a, q, s, gs)
+    sols = [sid for sid in pk.get_fp4_solutions(m, n, k, torch.bfloat16, torch.bfloat16)
+            if "128" in pk.ops.solution_name(int(sid)) or "256" in pk.ops.solution_name(int(sid))]
+    assert len(sols) >= 2
+    outs = [pk.mul_nvfp4_a16(ac, b, sp, gsc, m, n, k, -1)]
+    for sid in sols:
+        outs.append(pk.mul_nvfp4_a16(ac, b, sp, gsc, m, n, k, int(sid)))
+    for o in outs:
+        assert orc.max_rel_err(o.float().cpu(), want) <= GEMM_TOL
+    # every tile shape computes the same sums up to fp32 accumulation order
+    for o in outs[1:]:
+        assert orc.max_rel_err(o.float().cpu(), outs[0].float().cpu()) <= GEMM_TOL
+
+
 def test_native_selftest_binary(pk):
     exe = os.path.join(ROOT, "tests", "native", "selftest")
     if not os.path.exists(exe):

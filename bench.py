@@ -320,37 +320,62 @@ def main():
     ms_step = t.item() / args.steps
     value = full_bytes / (ms_step * 1e-3) / 1e9
 
-    # ---- end to end: host activations in, host outputs out, every step
+    # ---- end to end: host activations in, host outputs out, every step.
+    # Three streams, double buffered: the H2D copy of step i+1 and the D2H copy of step
+    # i-1 run beside the GEMMs of step i (PCIe moves ~4 MB per step = 70 us if serialised
+    # on the compute stream, more than half a step).  Every step still copies its own
+    # inputs from pinned host memory and its own outputs back; the timed region ends
+    # only after the last D2H copy has finished.
     host_a = {k: v.cpu().pin_memory() for k, v in acts.items()}
-    dev_a = {k: torch.empty_like(v) for k, v in acts.items()}
-    host_c = [torch.empty((m, n), dtype=torch.bfloat16).pin_memory() for _, n, _, _ in shard]
+    nbuf = 2
+    dev_a = [{k: torch.empty_like(v) for k, v in acts.items()} for _ in range(nbuf)]
+    dev_c = [[torch.empty((m, n), dtype=torch.bfloat16, device=dev) for _, n, _, _ in shard]
+             for _ in range(nbuf)]
+    host_c = [[torch.empty((m, n), dtype=torch.bfloat16).pin_memory() for _, n, _, _ in shard]
+              for _ in range(nbuf)]
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_cmp = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+    for ev in ev_cmp + ev_out:
+        ev.record()
+
+    def layer_step_out(i, a_by_k, outs):
+        for j, (nm, n, k, kind, b, sp) in enumerate(layers[i % copies]):
+            pk.ops.mul_nvfp4_a16_out(outs[j], a_by_k[k], b, sp, gs, m, n, k, -1)
+            if kind == "row" and world > 1:
+                if symm is not None:
+                    buf = symm.buffer(m, n, torch.bfloat16, dev, j)
+                    buf.copy_(outs[j])
+                    outs[j].copy_(symm.reduce(buf))
+                else:
+                    dist.all_reduce(outs[j])
 
     def e2e_step(i):
-        for k in dev_a:
-            dev_a[k].copy_(host_a[k], non_blocking=True)
-        outs = layer_step(i, dev_a)
-        for h, c in zip(host_c, outs):
-            h.copy_(c, non_blocking=True)
+        b = i % nbuf
+        cur = torch.cuda.current_stream()
+        s_in.wait_event(ev_cmp[b])   # the GEMMs of step i-2 have consumed dev_a[b]
+        with torch.cuda.stream(s_in):
+            for k in dev_a[b]:
+                dev_a[b][k].copy_(host_a[k], non_blocking=True)
+            ev_in[b].record(s_in)
+        cur.wait_event(ev_in[b])
+        cur.wait_event(ev_out[b])    # the D2H copies of step i-2 have drained dev_c[b]
+        layer_step_out(i, dev_a[b], dev_c[b])
+        ev_cmp[b].record(cur)
+        s_out.wait_event(ev_cmp[b])
+        with torch.cuda.stream(s_out):
+            for h, c in zip(host_c[b], dev_c[b]):
+                h.copy_(c, non_blocking=True)
+            ev_out[b].record(s_out)
 
-    e2e_graphs = None
-    if graphs is not None:
-        try:
-            e2e_graphs = []
-            side = torch.cuda.Stream()
-            for i in range(copies):
-                gph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gph, stream=side):
-                    e2e_step(i)
-                e2e_graphs.append(gph)
-            sync()
-        except Exception:
-            e2e_graphs = None
+    def e2e_drain():
+        cur = torch.cuda.current_stream()
+        for ev in ev_out:
+            cur.wait_event(ev)
 
-    def e2e_timed(i):
-        if e2e_graphs is not None:
-            e2e_graphs[i % copies].replay()
-        else:
-            e2e_step(i)
+    # (the e2e leg is always eager: its cross-stream events are not capturable as is)
+    e2e_timed = e2e_step
 
     for i in range(args.warmup):
         e2e_timed(i)
@@ -358,6 +383,7 @@ def main():
     e0.record()
     for i in range(args.steps):
         e2e_timed(i)
+    e2e_drain()
     e1.record()
     sync()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -365,7 +391,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = full_bytes / (t.item() / args.steps * 1e-3) / 1e9
     h2d = sum(v.numel() * 2 for v in host_a.values())
-    d2h = sum(h.numel() * 2 for h in host_c)
+    d2h = sum(h.numel() * 2 for h in host_c[0])
 
     # ---- roofline of the dominant kernel (the stream-K GEMM), per launch, live
     per_launch = []

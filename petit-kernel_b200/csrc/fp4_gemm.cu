@@ -124,7 +124,8 @@ template <int MODE, int NTOK, int KS> struct Cfg {
 };
 
 struct Barriers {
-    uint64_t full[16];
+    uint64_t full[16];      // weights + scales of the stage landed (dequant warps wait)
+    uint64_t full_act[16];  // token tile of the stage landed (MMA issuer waits)
     uint64_t empty[16];     // weights/scales of the stage consumed (dequant warps)
     uint64_t empty_act[16]; // token tile of the stage consumed (MMA commit; both CTAs if CL)
     uint64_t a_full[8];
@@ -300,6 +301,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         prefetch_tensormap(&tmap_out);
         for (int i = 0; i < C::kStages; ++i) {
             mbar_init(&bars->full[i], 1);
+            mbar_init(&bars->full_act[i], 1);
             mbar_init(&bars->empty[i], C::kStageWarps);
             mbar_init(&bars->empty_act[i], CL ? 2 : 1);
         }
@@ -342,7 +344,9 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         //
         // Programmatic dependent launch: weights and scales are constants, so the
         // first ring-full of them is requested BEFORE griddepcontrol.wait, i.e. while
-        // the previous kernel on the stream is still draining; everything that may
+        // the previous kernel on the stream is still draining -- and because weights and
+        // token tile complete on separate barriers, the dequant warps already fill the
+        // TMEM A stages from them; everything that may
         // depend on that kernel (the token tile here, global_scale / workspace /
         // output in the epilogue warps) is touched only after the wait.
         const uint64_t pol_stream = policy_evict_first();
@@ -384,8 +388,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                             uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
                             trace_stage(args, it, do_w ? 0 : 1);
                             if (do_w) {
-                                mbar_arrive_expect_tx(&bars->full[s], C::kActBytes + w_stage_bytes +
-                                                                          sc_stage_bytes);
+                                mbar_arrive_expect_tx(&bars->full[s], w_stage_bytes + sc_stage_bytes);
                                 bulk_g2s_hint(st + C::kActBytes, w_src, w_stage_bytes,
                                               &bars->full[s], pol_stream);
                                 if (PETIT_DBG(args.debug_flags, 8u)) // experiment: no scale copy
@@ -399,9 +402,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                             }
                             // token tile: box {64 k, NTOK tokens, kSubs slabs}
                             if (do_act) {
+                                mbar_arrive_expect_tx(&bars->full_act[s], C::kActBytes);
                                 if (PETIT_DBG(args.debug_flags, 4u)) // experiment: no token-tile traffic
                                     asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(
-                                                     smem_u32(&bars->full[s])),
+                                                     smem_u32(&bars->full_act[s])),
                                                  "r"((uint32_t)C::kActBytes)
                                                  : "memory");
                                 else if (CL) {
@@ -411,11 +415,11 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                                     for (int sl = 0; sl < C::kSubs; ++sl)
                                         tma_load_3d_mc(st + sl * (NTOK * 128) +
                                                            cta_rank * (NTOK / 2) * 128,
-                                                       &tmap_act, &bars->full[s], 0,
+                                                       &tmap_act, &bars->full_act[s], 0,
                                                        g.m_tile * NTOK + cta_rank * (NTOK / 2),
                                                        k_slab + sl, (uint16_t)3);
                                 } else
-                                    tma_load_3d(st, &tmap_act, &bars->full[s], 0, g.m_tile * NTOK,
+                                    tma_load_3d(st, &tmap_act, &bars->full_act[s], 0, g.m_tile * NTOK,
                                                 k_slab);
                             }
                         }
@@ -447,7 +451,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 const uint32_t ph = (it / C::kStages) & 1;
                 const uint32_t ta = it % C::kAStages;
                 const uint32_t ta_ph = (it / C::kAStages) & 1;
-                mbar_wait(&bars->full[s], ph);      // token tile landed
+                mbar_wait(&bars->full_act[s], ph);  // token tile landed
                 mbar_wait(&bars->a_full[ta], ta_ph); // weights are in TMEM
                 tc_fence_after();
                 if (lane == 0) trace_stage(args, it, 5);
@@ -492,7 +496,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         uint32_t s = 0, ph = 0, ta = 0, ta_ph = 1; // ta_ph: parity to wait on a_empty
         uint32_t it_dbg = 0;
         if (args.trace && threadIdx.x == kFirstDequantWarp * 32) {
-            mbar_wait(&bars->full[0], 0);
+            mbar_wait(&bars->full_act[0], 0);
             trace_stamp(args, 3);
         }
         // The four k-slice warps of a lane quarter share one SM sub-partition and run

@@ -126,9 +126,11 @@ int get_context(cudaStream_t stream, Workspace *ws, int *num_sms) {
         Workspace w;
         cudaError_t e1 = cudaMalloc(&w.partials, gemm::workspace_partials_bytes());
         cudaError_t e2 = cudaMalloc(&w.counters, gemm::workspace_counters_bytes());
-        cudaError_t e3 =
-            e2 == cudaSuccess ? cudaMemset(w.counters, 0, gemm::workspace_counters_bytes())
-                              : e2;
+        // ordered on the caller's stream ahead of the first GEMM (a plain cudaMemset runs
+        // on the legacy stream, which non-blocking streams do not wait for)
+        cudaError_t e3 = e2 == cudaSuccess ? cudaMemsetAsync(w.counters, 0,
+                                                             gemm::workspace_counters_bytes(), stream)
+                                           : e2;
         cudaThreadExchangeStreamCaptureMode(&mode);
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
             cudaFree(w.partials);

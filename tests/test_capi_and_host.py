@@ -4,12 +4,14 @@ like the reference's, and the Python surface has the reference's signatures.
 No compute call needs a GPU here."""
 import ctypes
 import inspect
+import os
 import re
+import subprocess
 
 import pytest
 import torch
 
-from helpers import HEADER, ensure_built
+from helpers import HEADER, ROOT, ensure_built
 
 
 @pytest.fixture(scope="module")
@@ -159,3 +161,19 @@ def test_ops_reject_cpu_tensors_no_fallback():
         pk.repack_nvfp4(q, 128, 200)
     with pytest.raises(RuntimeError, match="groupsize = 16"):
         pk.process_nvfp4_scales(torch.zeros((128, 8), dtype=torch.float8_e4m3fn), 128, 256)
+
+
+def test_bench_matmul_cli_flag_errors():
+    """tools/bench_matmul keeps the reference CLI's flags and messages
+    (tools/benchmarks/matmul/main.cc:17-35,336-358); argument errors need no GPU."""
+    exe = os.path.join(ROOT, "tools", "bench_matmul")
+    if not os.path.exists(exe):
+        pytest.skip("bench_matmul not built")
+    r = subprocess.run([exe, "-backend", "hipblaslt"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unknown backend: hipblaslt" in r.stderr
+    r = subprocess.run([exe, "-btype", "fp16"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Invalid b type for backend 'petit'" in r.stderr
+    r = subprocess.run([exe, "-m", "16", "-n", "100", "-k", "256"], capture_output=True, text=True)
+    assert r.returncode == 1 and "k % 256" in r.stderr
+    r = subprocess.run([exe, "-atype", "bf16", "-ctype", "fp16"], capture_output=True, text=True)
+    assert r.returncode == 1

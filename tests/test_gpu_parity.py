@@ -391,3 +391,23 @@ def test_native_selftest_binary(pk):
         pytest.skip("native selftest not built")
     r = subprocess.run([exe, "quick"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_bench_matmul_cli_tune(pk):
+    """`bench_matmul -algo tune` lists every solution, prints the reference's result line
+    for the fastest five, and a printed id can be fed back through -algo."""
+    import re
+
+    exe = os.path.join(ROOT, "tools", "bench_matmul")
+    if not os.path.exists(exe):
+        pytest.skip("bench_matmul not built")
+    base = [exe, "-m", "16", "-n", "1024", "-k", "1024", "-atype", "bf16", "-ctype", "bf16",
+            "-btype", "nvfp4", "-warmup", "2", "-repeat", "5"]
+    r = subprocess.run(base + ["-algo", "tune"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Finished enumerating 5 algorithms" in r.stdout
+    lines = re.findall(r"Matmul 16x1024x1024 bf16:bf16\. Backend: petit, batch: 1, algorithm: "
+                       r"([0-9a-f]{16}), 5 times total [0-9.]+ ms\. [0-9.]+ TFLOPS", r.stdout)
+    assert len(lines) == 5
+    r2 = subprocess.run(base + ["-algo", lines[0]], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0 and f"algorithm: {lines[0]}" in r2.stdout

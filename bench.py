@@ -211,12 +211,31 @@ def main():
     acts = {k: torch.randn((m, k), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
             for k in {k for _, _, k, _ in shard}}
 
-    # row-parallel outputs: ncclAllReduce over NVLink (default), or with
-    # PETIT_TP_ALLREDUCE=symm a one-shot all-reduce over peer memory (torch symmetric
-    # memory); measured equal at TP 4/8 (gpurun_out bench_tp*_{symm,nccl}.log).
+    # row-parallel outputs (o, down): PETIT_TP_ALLREDUCE = peer (default) | nccl | symm
+    #   peer: the GEMM writes into a peer-mapped buffer and this package's one-shot
+    #         all-reduce kernel (csrc/allreduce.cu) sums all ranks' buffers over NVLink --
+    #         one PDL-chained launch, ~5 us of host time;
+    #   nccl: dist.all_reduce; symm: torch.ops.symm_mem.one_shot_all_reduce.
     symm = None
+    peer = None
     allreduce_kind = "none" if world == 1 else "nccl"
-    if world > 1 and os.environ.get("PETIT_TP_ALLREDUCE", "nccl") == "symm":
+    want_ar = os.environ.get("PETIT_TP_ALLREDUCE", "peer")
+    if world > 1 and want_ar == "peer":
+        try:
+            peer = petit_tp.PeerAllReduce()
+            for j, (nm, n, k, kind) in enumerate(shard):
+                if kind == "row":
+                    buf = peer.buffer(m, n, torch.bfloat16, dev, j)
+                    buf.zero_()
+                    peer.reduce(buf)
+            torch.cuda.synchronize()
+            allreduce_kind = "petit one-shot peer-memory all-reduce kernel (NVLink P2P)"
+        except Exception as exc:  # fall back to NCCL, loudly
+            if rank == 0:
+                print(f"[bench] peer-memory all-reduce unavailable ({exc}); using NCCL",
+                      file=sys.stderr)
+            peer = None
+    if world > 1 and want_ar == "symm":
         try:
             symm = petit_tp.SymmAllReduce()
             for j, (nm, n, k, kind) in enumerate(shard):
@@ -233,7 +252,11 @@ def main():
     def layer_step(i, a_by_k=acts, collective=True):
         outs = []
         for j, (nm, n, k, kind, b, sp) in enumerate(layers[i % copies]):
-            if kind == "row" and world > 1 and collective and symm is not None:
+            if kind == "row" and world > 1 and collective and peer is not None:
+                buf = peer.buffer(m, n, torch.bfloat16, dev, j)
+                pk.ops.mul_nvfp4_a16_out(buf, a_by_k[k], b, sp, gs, m, n, k, -1)
+                c = peer.reduce(buf)
+            elif kind == "row" and world > 1 and collective and symm is not None:
                 buf = symm.buffer(m, n, torch.bfloat16, dev, j)
                 pk.ops.mul_nvfp4_a16_out(buf, a_by_k[k], b, sp, gs, m, n, k, -1)
                 c = symm.reduce(buf)
@@ -342,6 +365,11 @@ def main():
 
     def layer_step_out(i, a_by_k, outs):
         for j, (nm, n, k, kind, b, sp) in enumerate(layers[i % copies]):
+            if kind == "row" and world > 1 and peer is not None:
+                buf = peer.buffer(m, n, torch.bfloat16, dev, j)
+                pk.ops.mul_nvfp4_a16_out(buf, a_by_k[k], b, sp, gs, m, n, k, -1)
+                peer.reduce(buf, out=outs[j])
+                continue
             pk.ops.mul_nvfp4_a16_out(outs[j], a_by_k[k], b, sp, gs, m, n, k, -1)
             if kind == "row" and world > 1:
                 if symm is not None:
@@ -448,7 +476,9 @@ def main():
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": round(e2e_value, 1), "unit": "GB/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
-        "gpu_launches": args.steps * len(shard),
+        # our own kernels in the timed region: the GEMMs, plus the peer all-reduce launches
+        "gpu_launches": args.steps * (len(shard) + (sum(1 for x in shard if x[3] == "row")
+                                                    if (world > 1 and peer is not None) else 0)),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "frac_of_hbm_peak_layer_set": round(value / (hbm_peak * world), 4),
     }

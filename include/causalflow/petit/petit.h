@@ -149,6 +149,24 @@ int petit_hal_copy_to_device(void *dst, const void *src, size_t bytes);
 int petit_hal_copy_to_host(void *dst, const void *src, size_t bytes);
 int petit_hal_synchronize(void);
 
+/* Tensor-parallel extension (SURVEY section 8 rows e/f2; no reference counterpart): one-shot
+ * all-reduce (sum) of a small 16-bit tensor over peer-mapped (symmetric) memory.
+ * peer_bufs[r] / peer_pads[r] are THIS process's mappings of rank r's data buffer and
+ * signal pad (petit_allreduce_pad_bytes() bytes, zeroed once, then owned by this
+ * function); epoch is a local zero-initialised device buffer of
+ * petit_allreduce_epoch_bytes().  Every rank must call it with the same numel, in the
+ * same order per pad.  out must not alias the local buffer.  dtype: PETIT_DTYPE_BF16/FP16;
+ * numel % 8 == 0; world <= 8.  end_barrier != 0: the local buffer may be overwritten as
+ * soon as the call has completed on the stream; end_barrier == 0 (one NVLink round trip
+ * less): only after the NEXT call of this group has completed, i.e. the caller alternates
+ * between two buffers (each with its own pad and epoch).  A peer that never arrives traps
+ * the kernel after ~4 s. */
+size_t petit_allreduce_pad_bytes(void);
+size_t petit_allreduce_epoch_bytes(void);
+int petit_allreduce_oneshot(void *out, const void *const *peer_bufs, void *const *peer_pads,
+                            void *epoch, int rank, int world, size_t numel, int dtype,
+                            int end_barrier, petit_stream_t stream);
+
 /* Version of the packed layouts produced by the repack functions. */
 int petit_packed_layout_version(void);
 /* Human-readable name of a solution id ("" if unknown); pointer is static. */

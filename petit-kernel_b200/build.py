@@ -20,7 +20,7 @@ PKG = os.path.join(HERE, "petit_kernel")
 LIB = os.path.join(PKG, "libpetit_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["fp4_gemm.cu", "repack.cu", "capi.cu"]
+CU_SOURCES = ["fp4_gemm.cu", "repack.cu", "capi.cu", "allreduce.cu"]
 
 
 def _newer(target: str, deps: list[str]) -> bool:

@@ -390,6 +390,40 @@ PYBIND11_MODULE(ops, m) {
           py::arg("out"), py::arg("a"), py::arg("b"), py::arg("s"), py::arg("global_scale"),
           py::arg("size_m"), py::arg("size_n"), py::arg("size_k"), py::arg("solution_id") = -1);
 
+    // extras: tensor-parallel one-shot all-reduce over peer-mapped memory (petit_tp)
+    m.def(
+        "allreduce_oneshot",
+        [](const torch::Tensor &out, const std::vector<int64_t> &buf_ptrs,
+           const std::vector<int64_t> &pad_ptrs, const torch::Tensor &epoch, int64_t rank,
+           int64_t numel, bool end_barrier) {
+            TORCH_CHECK(out.is_cuda() && out.is_contiguous(), "out must be a contiguous CUDA tensor");
+            TORCH_CHECK(out.scalar_type() == torch::kBFloat16 || out.scalar_type() == torch::kHalf,
+                        "out must be bf16 or fp16");
+            TORCH_CHECK(buf_ptrs.size() == pad_ptrs.size() && !buf_ptrs.empty() && buf_ptrs.size() <= 8,
+                        "need one buffer and one pad pointer per rank (world <= 8)");
+            TORCH_CHECK(numel <= out.numel(), "out is smaller than numel");
+            TORCH_CHECK(epoch.is_cuda() && epoch.nbytes() >= petit_allreduce_epoch_bytes(),
+                        "epoch buffer too small");
+            const void *bufs[8];
+            void *pads[8];
+            for (size_t r = 0; r < buf_ptrs.size(); ++r) {
+                bufs[r] = reinterpret_cast<const void *>(buf_ptrs[r]);
+                pads[r] = reinterpret_cast<void *>(pad_ptrs[r]);
+            }
+            c10::cuda::CUDAGuard guard(out.device());
+            int rc = petit_allreduce_oneshot(
+                out.data_ptr(), bufs, pads, epoch.data_ptr(), (int)rank, (int)buf_ptrs.size(),
+                (size_t)numel,
+                out.scalar_type() == torch::kBFloat16 ? PETIT_DTYPE_BF16 : PETIT_DTYPE_FP16,
+                end_barrier ? 1 : 0, at::cuda::getCurrentCUDAStream(out.device().index()).stream());
+            TORCH_CHECK(rc == 0, "petit_allreduce_oneshot failed with code ", rc);
+            return out;
+        },
+        py::arg("out"), py::arg("buf_ptrs"), py::arg("pad_ptrs"), py::arg("epoch"), py::arg("rank"),
+        py::arg("numel"), py::arg("end_barrier") = true);
+    m.def("allreduce_pad_bytes", []() { return (int64_t)petit_allreduce_pad_bytes(); });
+    m.def("allreduce_epoch_bytes", []() { return (int64_t)petit_allreduce_epoch_bytes(); });
+
     // extras: round-trip / bit-exactness hooks and introspection
     m.def("unpack_fp4", &UnpackFp4, "Inverse of repack_nvfp4 (test hook)");
     m.def("dequant_dense", &DequantDense, "Dense dequantisation hook", py::arg("w"),

@@ -94,6 +94,66 @@ class SymmAllReduce:
         return torch.ops.symm_mem.one_shot_all_reduce(buf, "sum", self.group.group_name)
 
 
+class PeerAllReduce:
+    """One-shot all-reduce of small row-parallel outputs with this package's own kernel
+    (csrc/allreduce.cu) over torch symmetric memory: the GEMM writes its partial [M, N]
+    into a peer-mapped buffer (`buffer()`), `reduce()` launches ONE kernel that exchanges
+    per-CTA flags with the peers, sums all ranks' buffers through NVLink in rank order
+    (bit-identical on every rank) and releases the buffer.  ~5 us of host time per call
+    (no NCCL, no dispatcher), chained to the GEMMs with programmatic dependent launch."""
+
+    def __init__(self, group=None):
+        import petit_kernel as pk  # CUDA extension; no fallback
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.pk = pk
+        self.symm_mem = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.slots = {}
+        self.by_ptr = {}
+
+    def _alloc(self, m: int, n: int, dtype, device):
+        pad_elems = self.pk.ops.allreduce_pad_bytes() // 2
+        numel = m * n
+        data_elems = (numel + 127) // 128 * 128  # keep the pad 256-byte aligned
+        raw = self.symm_mem.empty((data_elems + pad_elems,), dtype=dtype, device=device)
+        raw.zero_()
+        hdl = self.symm_mem.rendezvous(raw, self.group.group_name)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)  # every pad is zero before anyone signals
+        esz = raw.element_size()
+        bufs = [int(hdl.buffer_ptrs[r]) for r in range(self.world)]
+        pads = [b + data_elems * esz for b in bufs]
+        epoch = torch.zeros(self.pk.ops.allreduce_epoch_bytes() // 4, dtype=torch.int32,
+                            device=device)
+        view = raw[:numel].view(m, n)
+        self.by_ptr[view.data_ptr()] = (view, bufs, pads, epoch, raw, hdl)
+        return view
+
+    def buffer(self, m: int, n: int, dtype, device, slot: int = 0) -> torch.Tensor:
+        """The buffer the next GEMM of this (shape, slot) must write.  Two buffers alternate
+        per call, which is what lets `reduce` skip the closing peer barrier: call it once
+        per GEMM, on every rank in the same order."""
+        key = (m, n, dtype, slot)
+        if key not in self.slots:
+            self.slots[key] = [[self._alloc(m, n, dtype, device) for _ in range(2)], 0]
+        pair = self.slots[key]
+        pair[1] ^= 1
+        return pair[0][pair[1]]
+
+    def reduce(self, buf: torch.Tensor, out: "torch.Tensor | None" = None) -> torch.Tensor:
+        entry = self.by_ptr.get(buf.data_ptr())
+        if entry is None:
+            raise ValueError("buf was not allocated by PeerAllReduce.buffer()")
+        view, bufs, pads, epoch = entry[:4]
+        if out is None:
+            out = torch.empty_like(view)
+        return self.pk.ops.allreduce_oneshot(out, bufs, pads, epoch, self.rank, view.numel(),
+                                             False)
+
+
 @dataclass
 class PackedLinear:
     """One FP4 linear layer resident on the current CUDA device."""
@@ -122,6 +182,12 @@ class PackedLinear:
         import petit_kernel as pk
 
         m = a.shape[0]
+        if self.kind == "row" and reduce and isinstance(symm, PeerAllReduce):
+            out = symm.buffer(m, self.n, a.dtype, a.device, slot)
+            mul_out = (pk.ops.mul_nvfp4_a16_out if self.fmt == "nvfp4"
+                       else pk.ops.mul_mxfp4_a16_out)
+            mul_out(out, a, self.b, self.s, self.global_scale, m, self.n, self.k, -1)
+            return symm.reduce(out)
         if self.kind == "row" and reduce and symm is not None and symm.ok:
             out = symm.buffer(m, self.n, a.dtype, a.device, slot)
             mul_out = (pk.ops.mul_nvfp4_a16_out if self.fmt == "nvfp4"

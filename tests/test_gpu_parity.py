@@ -6,6 +6,7 @@ weights; GEMM max rel err <= 1e-2 vs fp32 accumulation of the dequantised weight
 (tests/ops/test_fp4_gemm_quark.py:54) and its C++ matcher on the reference's sizes."""
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -411,3 +412,47 @@ def test_bench_matmul_cli_tune(pk):
     assert len(lines) == 5
     r2 = subprocess.run(base + ["-algo", lines[0]], capture_output=True, text=True, timeout=300)
     assert r2.returncode == 0 and f"algorithm: {lines[0]}" in r2.stdout
+
+
+@pytest.mark.parametrize("end_barrier", [True, False])
+def test_peer_allreduce_two_ranks_emulated_on_one_gpu(pk, end_barrier):
+    """csrc/allreduce.cu with world = 2 emulated on one device: both 'ranks' run as
+    concurrent kernels on two streams and exchange flags through each other's pads.
+    Result must be the fp32 sum in rank order, bit-identical on both ranks, for several
+    calls in a row (monotonic flag counters)."""
+    m, n = 16, 2048
+    numel = m * n
+    g = torch.Generator(device="cpu").manual_seed(5)
+    pad_words = pk.ops.allreduce_pad_bytes() // 4
+    pads = [torch.zeros(pad_words, dtype=torch.int32, device="cuda") for _ in range(2)]
+    epochs = [torch.zeros(pk.ops.allreduce_epoch_bytes() // 4, dtype=torch.int32, device="cuda")
+              for _ in range(2)]
+    bufs = [torch.empty((m, n), dtype=torch.bfloat16, device="cuda") for _ in range(2)]
+    outs = [torch.empty((m, n), dtype=torch.bfloat16, device="cuda") for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for it in range(4):
+        vals = [torch.randn((m, n), generator=g).to(torch.bfloat16) for _ in range(2)]
+        for r in range(2):
+            bufs[r].copy_(vals[r])
+        torch.cuda.synchronize()
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                pk.ops.allreduce_oneshot(outs[r], [b.data_ptr() for b in bufs],
+                                         [p.data_ptr() for p in pads], epochs[r], r, numel,
+                                         end_barrier)
+        torch.cuda.synchronize()
+        want = (vals[0].float() + vals[1].float()).to(torch.bfloat16)
+        assert torch.equal(outs[0].cpu(), want) and torch.equal(outs[1].cpu(), want), it
+    assert int(epochs[0][0]) == 4 and int(epochs[1][0]) == 4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_allreduce_two_gpus(pk):
+    """World-2 torchrun: PeerAllReduce (own kernel over symmetric memory) equals
+    ncclAllReduce on a row-parallel NVFP4 layer."""
+    script = os.path.join(ROOT, "tests", "tp_peer_allreduce_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                        "29541", script], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "PEER_ALLREDUCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -620,6 +620,11 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             float pre[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) pre[j] = 0.f;
+            // A tile split over many CTAs (small TP shards: 10 n-tiles on 148 SMs) would cost
+            // one L2 round trip per contributor in the register path below; from 4
+            // contributors on, the first 16 tokens go through the ring like the rest.
+            constexpr uint32_t kRingFit = (uint32_t)(C::kStages * C::kStageBytes) / (NTOK * kTileN * 4);
+            const uint32_t ring_from = (is_reducer && b_last - b_first > 3u && b_last - b_first <= kRingFit) ? 0u : 16u;
             const bool last_seg = u + (g.kt1 - g.kt0) >= u_end;
             if (ew_tid == 0 && last_seg) trace_stamp(args, 11);
             if (is_reducer) {
@@ -636,7 +641,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 }
                 named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
 #pragma unroll 1
-                for (uint32_t b = b_first + 1; b <= b_last; ++b) {
+                for (uint32_t b = b_first + 1; b <= b_last && ring_from != 0; ++b) {
                     const float *p = args.ws_partials +
                                      (size_t)(b * sched.n_mul + sched.n_add) * (kTileN * NTOK) + row;
                     float x[16];
@@ -655,19 +660,18 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             // its MMAs are complete, so the whole stage ring is idle -- the contributors'
             // partial tiles (tokens 16..m_valid) are pulled into it with one bulk copy each
             // (one L2 round trip in total instead of one per 16-token group).
-            constexpr uint32_t kRingFit = (uint32_t)(C::kStages * C::kStageBytes) / (NTOK * kTileN * 4);
-            const uint32_t n_ring = (is_reducer && m_valid > 16u)
+            const uint32_t n_ring = (is_reducer && m_valid > ring_from)
                                         ? (b_last - b_first < kRingFit ? b_last - b_first : kRingFit)
                                         : 0u;
             if (n_ring && ew_tid == 0) {
-                const uint32_t bytes = (m_valid - 16u) * (kTileN * 4);
+                const uint32_t bytes = (m_valid - ring_from) * (kTileN * 4);
                 mbar_arrive_expect_tx(&bars->part_full, n_ring * bytes);
                 for (uint32_t i = 0; i < n_ring; ++i)
-                    bulk_g2s(stage_base + (size_t)i * (NTOK * kTileN * 4) + 16 * kTileN * 4,
+                    bulk_g2s(stage_base + (size_t)i * (NTOK * kTileN * 4) + ring_from * kTileN * 4,
                              args.ws_partials +
                                  (size_t)((b_first + 1 + i) * sched.n_mul + sched.n_add) *
                                      (kTileN * NTOK) +
-                                 16 * kTileN,
+                                 ring_from * kTileN,
                              bytes, &bars->part_full);
             }
 #pragma unroll 1
@@ -698,12 +702,12 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                             __stcg(&slot[(size_t)(c0 + j) * kTileN + row], v[j]);
                     continue;
                 }
-                if (is_reducer && c0 == 0) {
+                if (is_reducer && (uint32_t)c0 < ring_from) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += pre[j];
                 } else if (is_reducer && !PETIT_DBG(args.debug_flags, 32u)) {
                     if (n_ring) {
-                        if (c0 == 16) {
+                        if ((uint32_t)c0 == ring_from) {
                             while (!mbar_try_wait(&bars->part_full, 0)) __nanosleep(32);
                         }
 #pragma unroll 1

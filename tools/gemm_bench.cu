@@ -36,8 +36,13 @@ int main(int argc, char **argv) {
     int reps = argc > 3 ? atoi(argv[3]) : 40;
     const char *only = argc > 4 ? argv[4] : "";
     struct Shape { const char *name; unsigned n, k; };
-    const Shape shapes[] = {{"qkv", 10240, 8192}, {"o", 8192, 8192}, {"gate_up", 57344, 8192},
-                            {"down", 8192, 28672}};
+    // the four 70B shapes, their TP-8 shards, or any "NxK" given on the command line
+    std::vector<Shape> shapes = {{"qkv", 10240, 8192},    {"o", 8192, 8192},
+                                 {"gate_up", 57344, 8192}, {"down", 8192, 28672},
+                                 {"qkv_tp8", 1280, 8192},  {"o_tp8", 8192, 1024},
+                                 {"gate_up_tp8", 7168, 8192}, {"down_tp8", 8192, 3584}};
+    unsigned cn = 0, ck = 0;
+    if (sscanf(only, "%ux%u", &cn, &ck) == 2) shapes.push_back({only, cn, ck});
     std::vector<unsigned> ms = {1, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192};
     if (argc > 5) { ms.clear(); ms.push_back(atoi(argv[5])); }
     const double hbm_peak = 6535.7, tf_peak = 1600.2;

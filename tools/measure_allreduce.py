@@ -1,4 +1,5 @@
-"""All-reduce cost at TP-N, alone and behind a row-parallel GEMM (run under torchrun):\n    torchrun --nproc-per-node 2 tools/measure_allreduce.py"""
+"""All-reduce cost at TP-N, alone and behind a row-parallel GEMM (run under torchrun):
+    torchrun --nproc-per-node 2 tools/measure_allreduce.py"""
 import os, sys, time, torch, torch.distributed as dist
 sys.path.insert(0, "petit-kernel_b200"); sys.path.insert(0, ".")
 import petit_kernel as pk, petit_tp

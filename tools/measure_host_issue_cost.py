@@ -1,4 +1,5 @@
-"""Host-side issue cost of one GEMM call through the Python API (run on a GPU box):\n    python tools/measure_host_issue_cost.py"""
+"""Host-side issue cost of one GEMM call through the Python API (run on a GPU box):
+    python tools/measure_host_issue_cost.py"""
 import sys, time, torch
 sys.path.insert(0, "petit-kernel_b200"); sys.path.insert(0, ".")
 import petit_kernel as pk

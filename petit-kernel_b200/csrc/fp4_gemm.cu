@@ -674,6 +674,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                                  ring_from * kTileN,
                              bytes, &bars->part_full);
             }
+            if (ew_tid == 0 && seg == 1) trace_stamp(args, 9); // a mid-kernel tile: epilogue begin
 #pragma unroll 1
             for (int c0 = 0; c0 < NTOK; c0 += 16) {
                 if ((uint32_t)c0 >= m_valid) break; // tokens beyond M are never stored
@@ -694,7 +695,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
                 }
-                if (ew_tid == 0 && last_seg && c0 == 0) trace_stamp(args, 9);
                 if (is_contrib) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
@@ -714,10 +714,13 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         for (uint32_t i = 0; i < n_ring; ++i) {
                             const uint32_t src = smem_u32(stage_base) + i * (NTOK * kTileN * 4) +
                                                  (uint32_t)c0 * (kTileN * 4) + row * 4;
+                            // all 16 loads first, then the adds; tokens >= m_valid read stale
+                            // ring bytes into lanes that the TMA store clips
+                            uint32_t x[16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if ((uint32_t)(c0 + j) < m_valid)
-                                    v[j] += __uint_as_float(lds_u32(src + j * (kTileN * 4)));
+                            for (int j = 0; j < 16; ++j) x[j] = lds_u32(src + j * (kTileN * 4));
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(x[j]);
                         }
                     }
                     // partial tiles that did not fit the ring (tile split over many CTAs):
@@ -743,11 +746,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     uint16_t *stg = reinterpret_cast<uint16_t *>(out_stage + out_buf * C::kOutStageBytes);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) stg[j * kTileN + row] = to_bits16<C::kIsBf16>(v[j] * gs);
-                    fence_proxy_async();
-                    if (ew_tid == 0 && last_seg && c0 == 0) trace_stamp(args, 10);
-                    if (ew_tid == 0) bulk_wait_group_read<1>();
+                    if (!PETIT_DBG(args.debug_flags, 256u)) fence_proxy_async();
+                    if (ew_tid == 0 && !PETIT_DBG(args.debug_flags, 128u)) bulk_wait_group_read<1>();
                     named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
-                    if (ew_tid == 0) {
+                    if (ew_tid == 0 && !PETIT_DBG(args.debug_flags, 512u)) {
                         tma_store_2d(&tmap_out, stg, (int)(g.n_tile * kTileN), (int)(m0 + c0));
                         bulk_commit_group();
                     }
@@ -759,6 +761,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+            if (ew_tid == 0 && seg == 1) trace_stamp(args, 10); // ... and end
 
             if (is_contrib) {
                 // publish: CTA barrier, then one release-increment of the tile counter

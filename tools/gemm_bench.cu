@@ -199,7 +199,7 @@ int main(int argc, char **argv) {
                 for (int b = 0; b < 160; ++b) if (tr[0][b * 16]) t0 = std::min(t0, tr[0][b * 16]);
                 const char *names[16] = {"entry", "setup_done", "griddep_wait_done", "first_stage_landed",
                                         "dequant_done", "mma_issued_all", "last_acc_full", "epilogue_done", "exit",
-                                        "lastseg_chains_summed", "lastseg_group0_staged", "lastseg_epi_begin", "lastseg_polled",
+                                        "seg1_epilogue_begin", "seg1_epilogue_end", "lastseg_epi_begin", "lastseg_polled",
                                         "lastseg_prefetched", "lastseg_ldtm0_done", "lastseg_group0_stored"};
                 for (int j = 0; j < 2; ++j) {
                     printf("  launch %d (us since launch-0 first entry): event min/avg/max\n", j);

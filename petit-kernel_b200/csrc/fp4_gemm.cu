@@ -68,6 +68,7 @@ constexpr int kKSlices = kNumDequantWarps / 4; // dequant warps per lane quarter
 constexpr int kRegsLight = 40, kRegsDequant = 88;
 constexpr int kEpilogueBarId = 1;
 constexpr int kSetupBarId = 2;
+constexpr int kTeamBarId0 = 3; // 3, 4, 5: one named barrier per epilogue team
 constexpr int kSmemBudget = 227 * 1024;
 
 template <int MODE, int NTOK, int KS> struct Cfg {
@@ -85,8 +86,13 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     static constexpr int kBarrierBytes = 1024;
     // epilogue staging: three [16 tokens][128 rows] 16-bit tiles feeding TMA stores
     static constexpr int kOutStageBytes = 16 * 128 * 2;
-    static constexpr int kOutBufs = 3;
-    static constexpr int kOutBytes = kOutBufs * kOutStageBytes;
+    // 256-token tiles have one accumulator, so their epilogue (16 groups) is exposed between
+    // tiles (measured 8.8 of 57 us per tile): there the 8 dequant warps that prefill leaves
+    // idle (kUsedSlices below) form two more epilogue teams and the groups are dealt round
+    // robin to the three teams, each with its own staging buffers.
+    static constexpr int kEpiTeams = NTOK >= 256 ? 3 : 1;
+    static constexpr int kOutBufs = kEpiTeams > 1 ? 2 : 3; // per team
+    static constexpr int kOutBytes = kEpiTeams * kOutBufs * kOutStageBytes;
     static constexpr int kRingBudget = kSmemBudget - kBarrierBytes - kOutBytes - 1024;
     static constexpr int kStages = kRingBudget / kStageBytes > 16 ? 16 : kRingBudget / kStageBytes;
     // Small-N MMAs that accumulate into the same TMEM columns serialise on the
@@ -311,7 +317,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->acc_full[i], 1);
-            mbar_init(&bars->acc_empty[i], kNumEpilogueWarps);
+            mbar_init(&bars->acc_empty[i], kNumEpilogueWarps * C::kEpiTeams);
         }
         mbar_init(&bars->part_full, 1);
         fence_mbar_init();
@@ -577,10 +583,21 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             u += g.kt1 - g.kt0;
         }
         if (threadIdx.x == kFirstDequantWarp * 32) trace_stamp(args, 4);
-    } else if (warp >= kFirstEpilogueWarp && warp < kFirstDequantWarp) {
+    } else if ((warp >= kFirstEpilogueWarp && warp < kFirstDequantWarp) ||
+               (C::kEpiTeams > 1 && warp >= kFirstDequantWarp + 4 * C::kUsedSlices)) {
         // ===================== epilogue warps =====================
+        // team 0 = warps 4-7; with kEpiTeams == 3 the idle dequant warps 16-19 / 20-23 are
+        // teams 1 / 2.  A team's four warps cover the four TMEM lane quarters.
         const uint32_t quarter = warp % 4;
-        const uint32_t ew_tid = threadIdx.x - kFirstEpilogueWarp * 32; // 0..127
+        const uint32_t team = warp < kFirstDequantWarp
+                                  ? 0u
+                                  : 1u + (warp - kFirstDequantWarp - 4 * C::kUsedSlices) / 4;
+        const uint32_t ew_tid = (warp % 4) * 32 + lane; // 0..127 inside the team
+        const bool lead = team == 0 && ew_tid == 0;      // the one thread that polls / publishes
+        constexpr int kAllEpiThreads = kNumEpilogueWarps * 32 * C::kEpiTeams;
+        const int team_bar = kTeamBarId0 + (int)team;
+        uint8_t *team_stage = out_stage + team * (C::kOutBufs * C::kOutStageBytes);
+        bool ring_ready = false;
         const uint32_t row = quarter * 32 + lane;
         const uint32_t lane_base = (quarter * 32) << 16;
         griddep_wait(); // global_scale, workspace and C may depend on the previous kernel
@@ -626,9 +643,9 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             constexpr uint32_t kRingFit = (uint32_t)(C::kStages * C::kStageBytes) / (NTOK * kTileN * 4);
             const uint32_t ring_from = (is_reducer && b_last - b_first > 3u && b_last - b_first <= kRingFit) ? 0u : 16u;
             const bool last_seg = u + (g.kt1 - g.kt0) >= u_end;
-            if (ew_tid == 0 && last_seg) trace_stamp(args, 11);
+            if (lead && last_seg) trace_stamp(args, 11);
             if (is_reducer) {
-                if (ew_tid == 0) {
+                if (lead) {
                     const uint32_t need = b_last - b_first;
                     uint32_t seen;
                     do {
@@ -639,9 +656,9 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     } while (seen < need);
                     if (last_seg) trace_stamp(args, 12);
                 }
-                named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
+                named_bar_sync(kEpilogueBarId, kAllEpiThreads);
 #pragma unroll 1
-                for (uint32_t b = b_first + 1; b <= b_last && ring_from != 0; ++b) {
+                for (uint32_t b = b_first + 1; b <= b_last && ring_from != 0 && team == 0; ++b) {
                     const float *p = args.ws_partials +
                                      (size_t)(b * sched.n_mul + sched.n_add) * (kTileN * NTOK) + row;
                     float x[16];
@@ -652,10 +669,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     for (int j = 0; j < 16; ++j) pre[j] += x[j];
                 }
             }
-            if (ew_tid == 0 && last_seg) trace_stamp(args, 13);
+            if (lead && last_seg) trace_stamp(args, 13);
             while (!mbar_try_wait(&bars->acc_full[acc], acc_ph)) __nanosleep(32);
             tc_fence_after();
-            if (ew_tid == 0 && last_seg) trace_stamp(args, 6);
+            if (lead && last_seg) trace_stamp(args, 6);
             // Reducer, tokens 16.. : the reducer segment is the LAST of this CTA's range and
             // its MMAs are complete, so the whole stage ring is idle -- the contributors'
             // partial tiles (tokens 16..m_valid) are pulled into it with one bulk copy each
@@ -663,7 +680,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             const uint32_t n_ring = (is_reducer && m_valid > ring_from)
                                         ? (b_last - b_first < kRingFit ? b_last - b_first : kRingFit)
                                         : 0u;
-            if (n_ring && ew_tid == 0) {
+            if (n_ring && lead) {
                 const uint32_t bytes = (m_valid - ring_from) * (kTileN * 4);
                 mbar_arrive_expect_tx(&bars->part_full, n_ring * bytes);
                 for (uint32_t i = 0; i < n_ring; ++i)
@@ -674,9 +691,9 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                                  ring_from * kTileN,
                              bytes, &bars->part_full);
             }
-            if (ew_tid == 0 && seg == 1) trace_stamp(args, 9); // a mid-kernel tile: epilogue begin
+            if (lead && seg == 1) trace_stamp(args, 9); // a mid-kernel tile: epilogue begin
 #pragma unroll 1
-            for (int c0 = 0; c0 < NTOK; c0 += 16) {
+            for (int c0 = (int)team * 16; c0 < NTOK; c0 += 16 * C::kEpiTeams) {
                 if ((uint32_t)c0 >= m_valid) break; // tokens beyond M are never stored
                 float v[16];
                 {
@@ -686,7 +703,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
                 }
-                if (ew_tid == 0 && last_seg && c0 == 0) trace_stamp(args, 14);
+                if (lead && last_seg && c0 == 0) trace_stamp(args, 14);
 #pragma unroll
                 for (int ch = 1; ch < C::kChains; ++ch) {
                     uint32_t r1[16];
@@ -707,8 +724,9 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     for (int j = 0; j < 16; ++j) v[j] += pre[j];
                 } else if (is_reducer && !PETIT_DBG(args.debug_flags, 32u)) {
                     if (n_ring) {
-                        if ((uint32_t)c0 == ring_from) {
+                        if (!ring_ready) {
                             while (!mbar_try_wait(&bars->part_full, 0)) __nanosleep(32);
+                            ring_ready = true;
                         }
 #pragma unroll 1
                         for (uint32_t i = 0; i < n_ring; ++i) {
@@ -743,45 +761,45 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     // map clips tokens >= M and rows >= N.  Three buffers in rotation: the
                     // wait below (before the barrier) leaves only the previous group's store
                     // in flight, so the buffer the NEXT group fills is known to be drained.
-                    uint16_t *stg = reinterpret_cast<uint16_t *>(out_stage + out_buf * C::kOutStageBytes);
+                    uint16_t *stg = reinterpret_cast<uint16_t *>(team_stage + out_buf * C::kOutStageBytes);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) stg[j * kTileN + row] = to_bits16<C::kIsBf16>(v[j] * gs);
                     if (!PETIT_DBG(args.debug_flags, 256u)) fence_proxy_async();
-                    if (ew_tid == 0 && !PETIT_DBG(args.debug_flags, 128u)) bulk_wait_group_read<1>();
-                    named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
+                    if (ew_tid == 0 && !PETIT_DBG(args.debug_flags, 128u))
+                        bulk_wait_group_read<C::kOutBufs - 2>();
+                    named_bar_sync(team_bar, kNumEpilogueWarps * 32);
                     if (ew_tid == 0 && !PETIT_DBG(args.debug_flags, 512u)) {
                         tma_store_2d(&tmap_out, stg, (int)(g.n_tile * kTileN), (int)(m0 + c0));
                         bulk_commit_group();
                     }
                     out_buf = out_buf == C::kOutBufs - 1 ? 0 : out_buf + 1;
                 }
-                if (ew_tid == 0 && last_seg && c0 == 0) trace_stamp(args, 15);
+                if (lead && last_seg && c0 == 0) trace_stamp(args, 15);
             }
             // accumulator drained -> MMA may reuse it
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
-            if (ew_tid == 0 && seg == 1) trace_stamp(args, 10); // ... and end
+            if (lead && seg == 1) trace_stamp(args, 10); // ... and end
 
             if (is_contrib) {
                 // publish: CTA barrier, then one release-increment of the tile counter
-                named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
-                if (ew_tid == 0)
+                named_bar_sync(kEpilogueBarId, kAllEpiThreads);
+                if (lead)
                     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(
                                      args.ws_counters + out_tile)
                                  : "memory");
             } else if (is_reducer) {
-                named_bar_sync(kEpilogueBarId, kNumEpilogueWarps * 32);
-                if (ew_tid == 0) args.ws_counters[out_tile] = 0; // self-cleaning
+                named_bar_sync(kEpilogueBarId, kAllEpiThreads);
+                if (lead) args.ws_counters[out_tile] = 0; // self-cleaning
             }
             u += g.kt1 - g.kt0;
         }
+        // staging smem must outlive the read of this team's last TMA store
+        if (ew_tid == 0) bulk_wait_group_read<0>();
     }
 
-    if (threadIdx.x == kFirstEpilogueWarp * 32) {
-        bulk_wait_group_read<0>(); // staging smem must outlive the last TMA store's read
-        trace_stamp(args, 7);
-    }
+    if (threadIdx.x == kFirstEpilogueWarp * 32) trace_stamp(args, 7);
     tc_fence_before();
     if (CL)
         cluster_sync(); // the peer may still multicast into / arrive on this CTA's smem

@@ -48,6 +48,14 @@ def headers() -> list[str]:
 def build_lib(force: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hs = headers()
+    # objects built with other flags (e.g. -DPETIT_DEBUG_HOOKS experiments) must not survive
+    flags = os.environ.get("PETIT_EXTRA_NVCC_FLAGS", "")
+    stamp = os.path.join(OBJ, ".flags")
+    old = open(stamp).read() if os.path.exists(stamp) else None
+    if old != flags:
+        force = True
+        with open(stamp, "w") as f:
+            f.write(flags)
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))

@@ -222,6 +222,12 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
             return e ? std::atoi(e) : 0;
         }();
         args.skew_cycles = (uint32_t)skew;
+        static const int tilt = [] {
+            const char *e = std::getenv("PETIT_TILT");
+            const int v = e ? std::atoi(e) : 0;
+            return v > 500 ? 500 : (v < -500 ? -500 : v);
+        }();
+        args.tilt_permille = tilt;
     }
     const int mode = d.elem_b == kElemMx
                          ? gemm::kModeMxBf16

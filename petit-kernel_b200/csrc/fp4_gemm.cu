@@ -150,13 +150,27 @@ struct Sched {
     uint32_t total_units; // < 2^31, checked by the launcher
     uint32_t grid;
     uint32_t n_mul, n_add; // this CTA's n-tile = n_mul * (tile / m_tiles) + n_add
+    // Range tilt (per mille, tuning knob PETIT_TILT, 0 = equal ranges): CTA b streams
+    // 1 + tilt * (1 - 2b/(grid-1)) of the average.  The hardware hands out CTAs in
+    // blockIdx order as SMs free up behind the previous kernel, so low ids start (and
+    // prefetch) earlier than high ids; the tilts of all CTAs sum to zero.
+    int32_t tilt;
 
     __device__ __forceinline__ uint32_t begin(uint32_t b) const {
-        return (uint32_t)((uint64_t)total_units * b / grid);
+        if (tilt == 0) return (uint32_t)((uint64_t)total_units * b / grid);
+        const int64_t wn = (int64_t)b * (grid - 1) * 1000 + (int64_t)tilt * b * (grid - b);
+        return (uint32_t)((uint64_t)total_units * (uint64_t)wn /
+                          ((uint64_t)grid * (grid - 1) * 1000));
     }
     // CTA that owns unit u (inverse of begin()).
     __device__ __forceinline__ uint32_t owner(uint32_t u) const {
-        return (uint32_t)((((uint64_t)u + 1) * grid - 1) / total_units);
+        if (tilt == 0) return (uint32_t)((((uint64_t)u + 1) * grid - 1) / total_units);
+        uint32_t lo = 0, hi = grid - 1; // smallest b with begin(b + 1) > u
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) / 2;
+            if (begin(mid + 1) > u) hi = mid; else lo = mid + 1;
+        }
+        return lo;
     }
 };
 
@@ -285,7 +299,14 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
     uint8_t *stage_base = out_stage + C::kOutBytes;
 
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    if (threadIdx.x == 0) trace_stamp(args, 0);
+    if (threadIdx.x == 0) {
+        trace_stamp(args, 0);
+        if (args.trace) { // which SM this CTA landed on (trace buffer: [160][16] + [64][8] + [160])
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            args.trace[160 * 16 + 64 * 8 + blockIdx.x] = smid;
+        }
+    }
     // Let the next kernel on the stream (if it was launched with programmatic stream
     // serialisation) start its prologue / weight prefetch on SMs as they free up.
     if (threadIdx.x == 0) griddep_launch_dependents();
@@ -299,6 +320,8 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
     sched.grid = CL ? gridDim.x / 2 : gridDim.x;
     sched.n_mul = CL ? 2 : 1;
     sched.n_add = cta_rank;
+    // only with enough units per range that no range can come out empty
+    sched.tilt = (sched.grid > 1 && sched.total_units >= 4 * sched.grid) ? args.tilt_permille : 0;
     const uint32_t u_begin = sched.begin(sched_id);
     const uint32_t u_end = sched.begin(sched_id + 1);
 
@@ -458,6 +481,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 const uint32_t ta = it % C::kAStages;
                 const uint32_t ta_ph = (it / C::kAStages) & 1;
                 mbar_wait(&bars->full_act[s], ph);  // token tile landed
+                if (it == 0 && lane == 0) trace_stamp(args, 3);
                 mbar_wait(&bars->a_full[ta], ta_ph); // weights are in TMEM
                 tc_fence_after();
                 if (lane == 0) trace_stage(args, it, 5);
@@ -501,10 +525,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         const uint32_t tmem_dst = tmem_a0 + ((quarter * 32) << 16) + c0 * 16;
         uint32_t s = 0, ph = 0, ta = 0, ta_ph = 1; // ta_ph: parity to wait on a_empty
         uint32_t it_dbg = 0;
-        if (args.trace && threadIdx.x == kFirstDequantWarp * 32) {
-            mbar_wait(&bars->full_act[0], 0);
-            trace_stamp(args, 3);
-        }
         // The four k-slice warps of a lane quarter share one SM sub-partition and run
         // identical code; in lockstep they all hit the ALU-heavy (F2FP/LOP3) and the
         // FMA-heavy (IMAD.HI/HMUL2) parts of the loop body together and each pipe

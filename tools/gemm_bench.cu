@@ -134,8 +134,8 @@ int main(int argc, char **argv) {
             }
             if (getenv("PETIT_TRACE")) {
                 unsigned long long *d_tr;
-                CK(cudaMalloc(&d_tr, (160 * 16 + 64 * 8) * 8));
-                CK(cudaMemset(d_tr, 0, (160 * 16 + 64 * 8) * 8));
+                CK(cudaMalloc(&d_tr, (160 * 16 + 64 * 8 + 160) * 8));
+                CK(cudaMemset(d_tr, 0, (160 * 16 + 64 * 8 + 160) * 8));
                 petit_debug_set_trace(d_tr);
                 for (int i = 0; i < 4; ++i) call(i); // back-to-back: the last launch's stamps survive
                 CK(cudaDeviceSynchronize());
@@ -175,7 +175,7 @@ int main(int argc, char **argv) {
             if (getenv("PETIT_TRACE2")) {
                 // two consecutive launches stamped into separate buffers on the common
                 // globaltimer base: shows how launch i+1 overlaps the tail of launch i
-                const size_t words = 160 * 16 + 64 * 8;
+                const size_t words = 160 * 16 + 64 * 8 + 160; // + one SM id per CTA
                 unsigned long long *d_tr[2];
                 for (int j = 0; j < 2; ++j) {
                     CK(cudaMalloc(&d_tr[j], words * 8));
@@ -214,6 +214,29 @@ int main(int argc, char **argv) {
                         if (cnt) printf("    %-20s %7.2f %7.2f %7.2f\n", names[e], mn, sum / cnt, mx2);
                     }
                     cudaFree(d_tr[j]);
+                }
+                // PETIT_TRACE_DUMP=<file>: one CSV row per CTA and launch (all 16 stamps in us
+                // since launch-0 first entry, 0 = not stamped) for offline straggler analysis
+                if (const char *dump = getenv("PETIT_TRACE_DUMP")) {
+                    FILE *f = fopen(dump, "a");
+                    if (f) {
+                        fprintf(f, "# %s %s %s M=%u N=%u K=%u: shape,m,launch,cta,smid", s.name,
+                                mx ? "mx" : "nv", bf16 ? "bf16" : "f16", m, s.n, s.k);
+                        for (int e = 0; e < 16; ++e) fprintf(f, ",%s", names[e]);
+                        fprintf(f, "\n");
+                        for (int j = 0; j < 2; ++j)
+                            for (int b = 0; b < 160; ++b) {
+                                if (!tr[j][b * 16]) continue;
+                                fprintf(f, "%s,%u,%d,%d,%llu", s.name, m, j, b,
+                                        tr[j][160 * 16 + 64 * 8 + b]);
+                                for (int e = 0; e < 16; ++e) {
+                                    unsigned long long v = tr[j][b * 16 + e];
+                                    fprintf(f, ",%.2f", v ? (double)((long long)(v - t0)) * 1e-3 : 0.0);
+                                }
+                                fprintf(f, "\n");
+                            }
+                        fclose(f);
+                    }
                 }
             }
             double bytes = (double)wbytes + sbytes + 2.0 * m * s.k + 2.0 * m * s.n + 4;

@@ -44,11 +44,15 @@ using namespace petit::dq;
 #ifndef PETIT_DECODE_GROUPS
 #define PETIT_DECODE_GROUPS 2
 #endif
+#ifndef PETIT_DECODE_GROUPS_NVBF16
+#define PETIT_DECODE_GROUPS_NVBF16 1
+#endif
 
 namespace {
 
 // Warp roles, aligned to warpgroups so setmaxnreg can rebalance registers:
-//   WG0:   warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-3 idle
+//   WG0:   warp 0 = TMA producer (weights), warp 1 = MMA issuer, warp 2 = TMA producer
+//          (token tiles), warp 3 idle
 //   WG1:   warps 4-7  = epilogue (one per TMEM lane quarter)
 //   WG2-5: warps 8-23 = dequant (4 per lane quarter -> 4 per SM sub-partition)
 // (Measured: putting the two single-thread roles on the highest warp ids instead
@@ -56,8 +60,9 @@ namespace {
 // against the dequant warps.)
 constexpr int kNumDequantWarps = 16;
 constexpr int kNumEpilogueWarps = 4;
-constexpr int kProducerWarp = 0;
+constexpr int kProducerWarp = 0;    // weights + scales
 constexpr int kMmaWarp = 1;
+constexpr int kActProducerWarp = 2; // token tiles
 constexpr int kFirstEpilogueWarp = 4;
 constexpr int kFirstDequantWarp = 8;
 constexpr int kNumWarps = kFirstDequantWarp + kNumDequantWarps;
@@ -114,7 +119,9 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     // NVFP4-bf16 gets no faster and spills at the 88-register cap, so it keeps 1 group).
     static constexpr int kGroups =
         kUsedSlices > kChunks ? kUsedSlices / kChunks
-                              : ((NTOK <= 64 && MODE != kModeNvBf16) ? PETIT_DECODE_GROUPS : 1);
+                              : (NTOK <= 64 ? (MODE != kModeNvBf16 ? PETIT_DECODE_GROUPS
+                                                                   : PETIT_DECODE_GROUPS_NVBF16)
+                                            : 1);
     static constexpr int kActiveSlices = kUsedSlices / kGroups;  // k-slice warps per stage
     static constexpr int kStageWarps = 4 * kActiveSlices;        // dequant warps per stage
     static_assert(kChunks % kActiveSlices == 0, "chunks must split evenly over the k-slices");
@@ -150,21 +157,24 @@ struct Sched {
     uint32_t total_units; // < 2^31, checked by the launcher
     uint32_t grid;
     uint32_t n_mul, n_add; // this CTA's n-tile = n_mul * (tile / m_tiles) + n_add
-    // Range tilt (per mille, tuning knob PETIT_TILT, 0 = equal ranges): CTA b streams
-    // 1 + tilt * (1 - 2b/(grid-1)) of the average.  The hardware hands out CTAs in
-    // blockIdx order as SMs free up behind the previous kernel, so low ids start (and
-    // prefetch) earlier than high ids; the tilts of all CTAs sum to zero.
-    int32_t tilt;
+    // Tail ramp (tuning knob PETIT_RAMP="R,D", default off): the last R CTAs get
+    // D*1/R .. D*R/R units less than the others.  The hardware hands out CTAs in blockIdx
+    // order as SMs free up behind the previous kernel on the stream, so the highest ids
+    // become resident last and cannot prefetch (profiles/r01_percta_summary.txt).
+    uint32_t ramp_n, ramp_d, ramp_sum; // ramp_sum = sum of all deficits
 
+    __device__ __forceinline__ uint32_t ramp_cum(uint32_t b) const { // deficits of CTAs < b
+        uint32_t c = 0;
+        for (uint32_t i = 1; i + (grid - ramp_n) <= b; ++i) c += ramp_d * i / ramp_n;
+        return c;
+    }
     __device__ __forceinline__ uint32_t begin(uint32_t b) const {
-        if (tilt == 0) return (uint32_t)((uint64_t)total_units * b / grid);
-        const int64_t wn = (int64_t)b * (grid - 1) * 1000 + (int64_t)tilt * b * (grid - b);
-        return (uint32_t)((uint64_t)total_units * (uint64_t)wn /
-                          ((uint64_t)grid * (grid - 1) * 1000));
+        if (ramp_n == 0) return (uint32_t)((uint64_t)total_units * b / grid);
+        return (uint32_t)(((uint64_t)total_units + ramp_sum) * b / grid) - ramp_cum(b);
     }
     // CTA that owns unit u (inverse of begin()).
     __device__ __forceinline__ uint32_t owner(uint32_t u) const {
-        if (tilt == 0) return (uint32_t)((((uint64_t)u + 1) * grid - 1) / total_units);
+        if (ramp_n == 0) return (uint32_t)((((uint64_t)u + 1) * grid - 1) / total_units);
         uint32_t lo = 0, hi = grid - 1; // smallest b with begin(b + 1) > u
         while (lo < hi) {
             const uint32_t mid = (lo + hi) / 2;
@@ -320,8 +330,15 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
     sched.grid = CL ? gridDim.x / 2 : gridDim.x;
     sched.n_mul = CL ? 2 : 1;
     sched.n_add = cta_rank;
-    // only with enough units per range that no range can come out empty
-    sched.tilt = (sched.grid > 1 && sched.total_units >= 4 * sched.grid) ? args.tilt_permille : 0;
+    // decode tiles only, and only with enough units per CTA that the ramp stays a small
+    // correction (every range keeps at least half of the average)
+    sched.ramp_n = sched.ramp_d = sched.ramp_sum = 0;
+    if (NTOK <= 64 && args.ramp_n != 0 && args.ramp_n < sched.grid &&
+        sched.total_units >= 2 * args.ramp_d * sched.grid) {
+        sched.ramp_n = args.ramp_n;
+        sched.ramp_d = args.ramp_d;
+        for (uint32_t i = 1; i <= args.ramp_n; ++i) sched.ramp_sum += args.ramp_d * i / args.ramp_n;
+    }
     const uint32_t u_begin = sched.begin(sched_id);
     const uint32_t u_end = sched.begin(sched_id + 1);
 
@@ -366,100 +383,90 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
     const uint32_t k_bytes_half = args.k / 2;
 
     if (warp < kFirstEpilogueWarp) setmaxnreg_dec<kRegsLight>();
-    if (warp == kProducerWarp) {
-        // ===================== TMA producer =====================
-        // The loop is executed by the whole (converged) warp so that every value is
-        // warp-uniform; only the async instructions are issued by one elected lane.
+    if (warp == kProducerWarp || warp == kActProducerWarp) {
+        // ===================== TMA producers =====================
+        // Two warps run the same stage loop, one per operand: warp 0 streams weights +
+        // scales (-> full[s]), warp 2 the token tiles (-> full_act[s]).  The loops are
+        // executed by the whole (converged) warp so that every value is warp-uniform; only
+        // the async instructions are issued by one elected lane.
         //
-        // Programmatic dependent launch: weights and scales are constants, so the
-        // first ring-full of them is requested BEFORE griddepcontrol.wait, i.e. while
-        // the previous kernel on the stream is still draining -- and because weights and
-        // token tile complete on separate barriers, the dequant warps already fill the
-        // TMEM A stages from them; everything that may
-        // depend on that kernel (the token tile here, global_scale / workspace /
-        // output in the epilogue warps) is touched only after the wait.
+        // Programmatic dependent launch: weights and scales are constants, so their warp
+        // never waits for the grid dependency -- it fills the ring while the previous
+        // kernel on the stream is still draining, and the dequant warps already fill the
+        // TMEM A stages from it.  The token tile may be that kernel's output: its warp
+        // starts with griddepcontrol.wait.  (With a single producer warp the ring-full of
+        // weight requests -- ~0.2 us per stage of issue work -- sat in front of the wait;
+        // a CTA that became resident late, behind the last CTAs of the previous grid,
+        // asked for its first token tile 1.6 us after the dependency had resolved:
+        // profiles/r01_percta_summary.txt.)
+        const bool do_w = warp == kProducerWarp, do_act = !do_w;
         const uint64_t pol_stream = policy_evict_first();
-        const uint32_t total_stages = (u_end - u_begin) * C::kStagesPerUnit;
-        const uint32_t early = total_stages < (uint32_t)C::kStages ? total_stages : C::kStages;
-        // pass 0: weights+scales of stages [0, early); pass 1: token tiles of the same
-        // stages (after the grid dependency resolved); pass 2: the rest, both.
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-            if (pass == 1) {
-                griddep_wait();
-                if (lane == 0) trace_stamp(args, 2);
-            }
-            const uint32_t it_lo = pass == 2 ? early : 0u;
-            const uint32_t it_hi = pass == 2 ? total_stages : early;
-            const bool do_w = pass != 1, do_act = pass != 0;
-            uint32_t it = 0;
-            for (uint32_t u = u_begin; u < u_end && it < it_hi;) {
-                const Segment g = make_segment(sched, u, u_end);
-                const uint32_t rows = tile_rows(args.n, g.n_tile);
-                const uint8_t *w_tile = args.w + (size_t)g.n_tile * kTileN * k_bytes_half;
-                const uint8_t *sc_tile =
-                    args.sc + (size_t)g.n_tile * kTileN * (args.k / 64) * C::kScPerSub;
-                const uint32_t w_stage_bytes = C::kChunks * rows * 16;
-                const uint32_t sc_stage_bytes = C::kSubs * rows * C::kScPerSub;
-                const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
-                const uint8_t *w_src = w_tile + (size_t)g.kt0 * rows * 128;
-                const uint8_t *sc_src = sc_tile + (size_t)g.kt0 * rows * 4 * C::kScPerSub;
-                int32_t k_slab = (int32_t)(g.kt0 * 4);
-                for (uint32_t i = 0; i < n_stage && it < it_hi; ++i, ++it) {
-                    if (it >= it_lo) {
-                        const uint32_t s = it % C::kStages;
-                        const uint32_t ph = (it / C::kStages) & 1;
-                        if (pass == 2) {
-                            mbar_wait(&bars->empty[s], ph ^ 1);
-                            mbar_wait(&bars->empty_act[s], ph ^ 1);
-                        }
-                        if (elect_one()) {
-                            uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
-                            trace_stage(args, it, do_w ? 0 : 1);
-                            if (do_w) {
-                                mbar_arrive_expect_tx(&bars->full[s], w_stage_bytes + sc_stage_bytes);
-                                bulk_g2s_hint(st + C::kActBytes, w_src, w_stage_bytes,
-                                              &bars->full[s], pol_stream);
-                                if (PETIT_DBG(args.debug_flags, 8u)) // experiment: no scale copy
-                                    asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(
-                                                     smem_u32(&bars->full[s])),
-                                                 "r"(sc_stage_bytes)
-                                                 : "memory");
-                                else
-                                bulk_g2s_hint(st + C::kActBytes + C::kWBytes, sc_src,
-                                              sc_stage_bytes, &bars->full[s], pol_stream);
-                            }
-                            // token tile: box {64 k, NTOK tokens, kSubs slabs}
-                            if (do_act) {
-                                mbar_arrive_expect_tx(&bars->full_act[s], C::kActBytes);
-                                if (PETIT_DBG(args.debug_flags, 4u)) // experiment: no token-tile traffic
-                                    asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(
-                                                     smem_u32(&bars->full_act[s])),
-                                                 "r"((uint32_t)C::kActBytes)
-                                                 : "memory");
-                                else if (CL) {
-                                    // my half of the token rows, one 128-byte-row slab per
-                                    // call, delivered to both CTAs of the cluster
+        if (do_act) {
+            griddep_wait();
+            if (lane == 0) trace_stamp(args, 2);
+        }
+        uint32_t it = 0;
+        for (uint32_t u = u_begin; u < u_end;) {
+            const Segment g = make_segment(sched, u, u_end);
+            const uint32_t rows = tile_rows(args.n, g.n_tile);
+            const uint8_t *w_tile = args.w + (size_t)g.n_tile * kTileN * k_bytes_half;
+            const uint8_t *sc_tile =
+                args.sc + (size_t)g.n_tile * kTileN * (args.k / 64) * C::kScPerSub;
+            const uint32_t w_stage_bytes = C::kChunks * rows * 16;
+            const uint32_t sc_stage_bytes = C::kSubs * rows * C::kScPerSub;
+            const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
+            const uint8_t *w_src = w_tile + (size_t)g.kt0 * rows * 128;
+            const uint8_t *sc_src = sc_tile + (size_t)g.kt0 * rows * 4 * C::kScPerSub;
+            int32_t k_slab = (int32_t)(g.kt0 * 4);
+            for (uint32_t i = 0; i < n_stage; ++i, ++it) {
+                const uint32_t s = it % C::kStages;
+                const uint32_t ph = (it / C::kStages) & 1;
+                if (it >= (uint32_t)C::kStages)
+                    mbar_wait(do_w ? &bars->empty[s] : &bars->empty_act[s], ph ^ 1);
+                if (elect_one()) {
+                    uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
+                    trace_stage(args, it, do_w ? 0 : 1);
+                    if (do_w) {
+                        mbar_arrive_expect_tx(&bars->full[s], w_stage_bytes + sc_stage_bytes);
+                        bulk_g2s_hint(st + C::kActBytes, w_src, w_stage_bytes,
+                                      &bars->full[s], pol_stream);
+                        if (PETIT_DBG(args.debug_flags, 8u)) // experiment: no scale copy
+                            asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(
+                                             smem_u32(&bars->full[s])),
+                                         "r"(sc_stage_bytes)
+                                         : "memory");
+                        else
+                        bulk_g2s_hint(st + C::kActBytes + C::kWBytes, sc_src,
+                                      sc_stage_bytes, &bars->full[s], pol_stream);
+                    } else {
+                        // token tile: box {64 k, NTOK tokens, kSubs slabs}
+                        mbar_arrive_expect_tx(&bars->full_act[s], C::kActBytes);
+                        if (PETIT_DBG(args.debug_flags, 4u)) // experiment: no token-tile traffic
+                            asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(
+                                             smem_u32(&bars->full_act[s])),
+                                         "r"((uint32_t)C::kActBytes)
+                                         : "memory");
+                        else if (CL) {
+                            // my half of the token rows, one 128-byte-row slab per
+                            // call, delivered to both CTAs of the cluster
 #pragma unroll
-                                    for (int sl = 0; sl < C::kSubs; ++sl)
-                                        tma_load_3d_mc(st + sl * (NTOK * 128) +
-                                                           cta_rank * (NTOK / 2) * 128,
-                                                       &tmap_act, &bars->full_act[s], 0,
-                                                       g.m_tile * NTOK + cta_rank * (NTOK / 2),
-                                                       k_slab + sl, (uint16_t)3);
-                                } else
-                                    tma_load_3d(st, &tmap_act, &bars->full_act[s], 0, g.m_tile * NTOK,
-                                                k_slab);
-                            }
-                        }
-                        __syncwarp();
+                            for (int sl = 0; sl < C::kSubs; ++sl)
+                                tma_load_3d_mc(st + sl * (NTOK * 128) +
+                                                   cta_rank * (NTOK / 2) * 128,
+                                               &tmap_act, &bars->full_act[s], 0,
+                                               g.m_tile * NTOK + cta_rank * (NTOK / 2),
+                                               k_slab + sl, (uint16_t)3);
+                        } else
+                            tma_load_3d(st, &tmap_act, &bars->full_act[s], 0, g.m_tile * NTOK,
+                                        k_slab);
                     }
-                    w_src += w_stage_bytes;
-                    sc_src += sc_stage_bytes;
-                    k_slab += C::kSubs;
                 }
-                u += g.kt1 - g.kt0;
+                __syncwarp();
+                w_src += w_stage_bytes;
+                sc_src += sc_stage_bytes;
+                k_slab += C::kSubs;
             }
+            u += g.kt1 - g.kt0;
         }
     } else if (warp == kMmaWarp) {
         // ===================== MMA issuer =====================
@@ -678,15 +685,27 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 }
                 named_bar_sync(kEpilogueBarId, kAllEpiThreads);
 #pragma unroll 1
-                for (uint32_t b = b_first + 1; b <= b_last && ring_from != 0 && team == 0; ++b) {
+                // Two contributors per round trip: all loads of a pair are in flight before
+                // the first add; the sum order stays CTA order.  (A reducer whose last
+                // contributor publishes at the very end has these L2 round trips on the
+                // kernel's critical path: profiles/r01_percta_summary.txt, `down`.)
+                for (uint32_t b = b_first + 1; b <= b_last && ring_from != 0 && team == 0; b += 2) {
                     const float *p = args.ws_partials +
                                      (size_t)(b * sched.n_mul + sched.n_add) * (kTileN * NTOK) + row;
-                    float x[16];
+                    const bool two = b + 1 <= b_last;
+                    const float *p2 = args.ws_partials +
+                                      (size_t)((b + 1) * sched.n_mul + sched.n_add) * (kTileN * NTOK) + row;
+                    float x[16], y[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         x[j] = (uint32_t)j < m_valid ? __ldcg(p + (size_t)j * kTileN) : 0.f;
 #pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        y[j] = (two && (uint32_t)j < m_valid) ? __ldcg(p2 + (size_t)j * kTileN) : 0.f;
+#pragma unroll
                     for (int j = 0; j < 16; ++j) pre[j] += x[j];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pre[j] += y[j];
                 }
             }
             if (lead && last_seg) trace_stamp(args, 13);

@@ -26,7 +26,7 @@ struct GemmArgs {
     uint32_t use_cluster;   // allow the 2-CTA multicast variant for 128/256-token tiles
     uint32_t use_pdl;       // launch with programmatic stream serialisation
     uint32_t skew_cycles;   // initial phase skew between k-slice warps (tuning knob)
-    int32_t tilt_permille;  // stream-K range tilt, |tilt| <= 500 (tuning knob, 0 = equal ranges)
+    uint32_t ramp_n, ramp_d; // stream-K tail ramp: the last ramp_n CTAs get up to ramp_d units less
     unsigned long long *trace; // optional [grid][16] globaltimer stamps (debug), else null
 };
 

@@ -47,6 +47,13 @@ using namespace petit::dq;
 #ifndef PETIT_DECODE_GROUPS_NVBF16
 #define PETIT_DECODE_GROUPS_NVBF16 1
 #endif
+// A/B switches for tools/build_variant.sh (defaults = the shipped configuration)
+#ifndef PETIT_REDUCER_PAIR
+#define PETIT_REDUCER_PAIR 1 // reducer loads two contributors' partials per L2 round trip
+#endif
+#ifndef PETIT_EPILOGUE_REGS88
+#define PETIT_EPILOGUE_REGS88 1 // epilogue warps take the 8 registers/thread the pool has left
+#endif
 
 namespace {
 
@@ -69,7 +76,7 @@ constexpr int kNumWarps = kFirstDequantWarp + kNumDequantWarps;
 constexpr int kNumThreads = kNumWarps * 32;
 constexpr int kKSlices = kNumDequantWarps / 4; // dequant warps per lane quarter
 // 768 threads x 80 registers = 61440 is the CTA pool setmaxnreg redistributes:
-// 128 x 40 (WG0) + 128 x 80 (epilogue) + 512 x 88 (dequant) = 60416 <= 61440.
+// 128 x 40 (WG0) + 128 x 88 (epilogue) + 512 x 88 (dequant / extra epilogue teams) = 61440.
 constexpr int kRegsLight = 40, kRegsDequant = 88;
 constexpr int kEpilogueBarId = 1;
 constexpr int kSetupBarId = 2;
@@ -96,9 +103,15 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     // idle (kUsedSlices below) form two more epilogue teams and the groups are dealt round
     // robin to the three teams, each with its own staging buffers.
     static constexpr int kEpiTeams = NTOK >= 256 ? 3 : 1;
-    static constexpr int kOutBufs = kEpiTeams > 1 ? 2 : 3; // per team
+    // decode tiles store at most four 16-token groups per tile: two buffers are enough
+    static constexpr int kOutBufs = (kEpiTeams > 1 || NTOK <= 64) ? 2 : 3; // per team
     static constexpr int kOutBytes = kEpiTeams * kOutBufs * kOutStageBytes;
-    static constexpr int kRingBudget = kSmemBudget - kBarrierBytes - kOutBytes - 1024;
+    // reducer: running sum of the other CTAs' partials for the first 16 tokens,
+    // [16 tokens][128 rows] fp32, each element private to one epilogue thread.  (Held in
+    // registers it was spilled to local memory, and those spills miss the small L1 that is
+    // left next to 227 KB of shared memory: +0.7 us on every reducer's exit path.)
+    static constexpr int kPreBytes = 16 * 128 * 4;
+    static constexpr int kRingBudget = kSmemBudget - kBarrierBytes - kOutBytes - kPreBytes - 1024;
     static constexpr int kStages = kRingBudget / kStageBytes > 16 ? 16 : kRingBudget / kStageBytes;
     // Small-N MMAs that accumulate into the same TMEM columns serialise on the
     // full MMA latency (~130 clk measured), so consecutive k-steps rotate over
@@ -131,7 +144,9 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     static constexpr int kACols = KS / 2;          // TMEM columns of one A stage
     static constexpr int kAStagesRaw = (512 - kAccCols) / kACols;
     static constexpr int kAStages = kAStagesRaw > 8 ? 8 : kAStagesRaw;
-    static constexpr int kSmemBytes = kBarrierBytes + kOutBytes + kStages * kStageBytes + 1024;
+    static constexpr int kSmemBytes =
+        kBarrierBytes + kOutBytes + kPreBytes + kStages * kStageBytes + 1024;
+    static_assert(kSmemBytes <= kSmemBudget, "shared memory budget");
     static_assert(kStages >= 2, "need at least two smem stages");
     static_assert(kAStages >= 2, "need at least two TMEM A stages");
 };
@@ -270,6 +285,14 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -306,7 +329,8 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     Barriers *bars = reinterpret_cast<Barriers *>(smem);
     uint8_t *out_stage = smem + C::kBarrierBytes;
-    uint8_t *stage_base = out_stage + C::kOutBytes;
+    const uint32_t pre_smem = smem_u32(out_stage + C::kOutBytes); // reducer pre-sums
+    uint8_t *stage_base = out_stage + C::kOutBytes + C::kPreBytes;
 
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     if (threadIdx.x == 0) {
@@ -613,6 +637,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
     } else if ((warp >= kFirstEpilogueWarp && warp < kFirstDequantWarp) ||
                (C::kEpiTeams > 1 && warp >= kFirstDequantWarp + 4 * C::kUsedSlices)) {
         // ===================== epilogue warps =====================
+        setmaxnreg_inc<kRegsDequant>();
         // team 0 = warps 4-7; with kEpiTeams == 3 the idle dequant warps 16-19 / 20-23 are
         // teams 1 / 2.  A team's four warps cover the four TMEM lane quarters.
         const uint32_t quarter = warp % 4;
@@ -661,9 +686,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             // for the first 16 tokens are summed (in CTA order) into registers while
             // the MMAs of this last segment are still running; the tail after
             // acc_full is then just TMEM read + add + store.
-            float pre[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pre[j] = 0.f;
+            const uint32_t pre_addr = pre_smem + row * 4; // + j * 512: this thread's 16 sums
             // A tile split over many CTAs (small TP shards: 10 n-tiles on 148 SMs) would cost
             // one L2 round trip per contributor in the register path below; from 4
             // contributors on, the first 16 tokens go through the ring like the rest.
@@ -689,12 +712,12 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 // the first add; the sum order stays CTA order.  (A reducer whose last
                 // contributor publishes at the very end has these L2 round trips on the
                 // kernel's critical path: profiles/r01_percta_summary.txt, `down`.)
-                for (uint32_t b = b_first + 1; b <= b_last && ring_from != 0 && team == 0; b += 2) {
+                for (uint32_t b = b_first + 1; b <= b_last && ring_from != 0 && team == 0;
+                     b += PETIT_REDUCER_PAIR ? 2 : 1) {
                     const float *p = args.ws_partials +
                                      (size_t)(b * sched.n_mul + sched.n_add) * (kTileN * NTOK) + row;
-                    const bool two = b + 1 <= b_last;
-                    const float *p2 = args.ws_partials +
-                                      (size_t)((b + 1) * sched.n_mul + sched.n_add) * (kTileN * NTOK) + row;
+                    const bool two = PETIT_REDUCER_PAIR && b + 1 <= b_last;
+                    const float *p2 = p + (size_t)sched.n_mul * (kTileN * NTOK);
                     float x[16], y[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
@@ -702,10 +725,14 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         y[j] = (two && (uint32_t)j < m_valid) ? __ldcg(p2 + (size_t)j * kTileN) : 0.f;
+                    const bool first = b == b_first + 1;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) pre[j] += x[j];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) pre[j] += y[j];
+                    for (int j = 0; j < 16; ++j) {
+                        float acc = first ? 0.f : lds_f32(pre_addr + j * (kTileN * 4));
+                        acc += x[j];
+                        acc += y[j];
+                        sts_f32(pre_addr + j * (kTileN * 4), acc);
+                    }
                 }
             }
             if (lead && last_seg) trace_stamp(args, 13);
@@ -760,7 +787,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 }
                 if (is_reducer && (uint32_t)c0 < ring_from) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += pre[j];
+                    for (int j = 0; j < 16; ++j) v[j] += lds_f32(pre_addr + j * (kTileN * 4));
                 } else if (is_reducer && !PETIT_DBG(args.debug_flags, 32u)) {
                     if (n_ring) {
                         if (!ring_ready) {

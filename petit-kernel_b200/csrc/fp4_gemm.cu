@@ -51,6 +51,15 @@ using namespace petit::dq;
 #ifndef PETIT_REDUCER_PAIR
 #define PETIT_REDUCER_PAIR 1 // reducer loads two contributors' partials per L2 round trip
 #endif
+#ifndef PETIT_LDTM_PAIR
+#define PETIT_LDTM_PAIR 0 // epilogue reads two accumulator chains per tcgen05.wait::ld
+#endif
+#ifndef PETIT_DIRECT_STORE16
+#define PETIT_DIRECT_STORE16 0 // 16-token tiles: store C straight from registers (no smem staging / TMA)
+#endif
+#ifndef PETIT_PRIME_STAGES
+#define PETIT_PRIME_STAGES 0 // >0: the weight stream pauses after this many stages until the first token tile is requested
+#endif
 #ifndef PETIT_EPILOGUE_REGS88
 #define PETIT_EPILOGUE_REGS88 1 // epilogue warps take the 8 registers/thread the pool has left
 #endif
@@ -161,6 +170,7 @@ struct Barriers {
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
     uint64_t part_full;     // reducer: partial tiles landed in the (drained) stage ring
+    uint64_t act_started;   // the first token tile has been requested (PETIT_PRIME_STAGES)
     uint32_t tmem_base;
     uint32_t flag;
 };
@@ -384,6 +394,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             mbar_init(&bars->acc_empty[i], kNumEpilogueWarps * C::kEpiTeams);
         }
         mbar_init(&bars->part_full, 1);
+        mbar_init(&bars->act_started, 1);
         fence_mbar_init();
     }
     if (warp == kMmaWarp) tmem_alloc(&bars->tmem_base, 512);
@@ -447,6 +458,11 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 const uint32_t ph = (it / C::kStages) & 1;
                 if (it >= (uint32_t)C::kStages)
                     mbar_wait(do_w ? &bars->empty[s] : &bars->empty_act[s], ph ^ 1);
+                // A CTA that becomes resident just before the dependency resolves would
+                // otherwise have a ring-full of weight copies queued in front of its first
+                // token tile.
+                if (PETIT_PRIME_STAGES > 0 && do_w && it == (uint32_t)PETIT_PRIME_STAGES)
+                    mbar_wait(&bars->act_started, 0);
                 if (elect_one()) {
                     uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
                     trace_stage(args, it, do_w ? 0 : 1);
@@ -483,6 +499,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         } else
                             tma_load_3d(st, &tmap_act, &bars->full_act[s], 0, g.m_tile * NTOK,
                                         k_slab);
+                        if (PETIT_PRIME_STAGES > 0 && it == 0) mbar_arrive(&bars->act_started);
                     }
                 }
                 __syncwarp();
@@ -762,21 +779,39 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             for (int c0 = (int)team * 16; c0 < NTOK; c0 += 16 * C::kEpiTeams) {
                 if ((uint32_t)c0 >= m_valid) break; // tokens beyond M are never stored
                 float v[16];
-                {
-                    uint32_t r0[16];
-                    tmem_ld_x16(tmem + lane_base + acc * C::kAccBufCols + c0, r0);
-                    tmem_wait_ld();
+                if (PETIT_LDTM_PAIR && C::kChains >= 2) {
+                    // two accumulator chains per TMEM round trip; same sum order as below
+                    const uint32_t t0 = tmem + lane_base + acc * C::kAccBufCols + c0;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
-                }
-                if (lead && last_seg && c0 == 0) trace_stamp(args, 14);
+                    for (int ch = 0; ch < C::kChains; ch += 2) {
+                        uint32_t r0[16], r1[16];
+                        tmem_ld_x16(t0 + ch * NTOK, r0);
+                        tmem_ld_x16(t0 + (ch + 1) * NTOK, r1);
+                        tmem_wait_ld();
 #pragma unroll
-                for (int ch = 1; ch < C::kChains; ++ch) {
-                    uint32_t r1[16];
-                    tmem_ld_x16(tmem + lane_base + acc * C::kAccBufCols + ch * NTOK + c0, r1);
-                    tmem_wait_ld();
+                        for (int j = 0; j < 16; ++j) {
+                            v[j] = ch == 0 ? __uint_as_float(r0[j]) : v[j] + __uint_as_float(r0[j]);
+                            v[j] += __uint_as_float(r1[j]);
+                        }
+                    }
+                    if (lead && last_seg && c0 == 0) trace_stamp(args, 14);
+                } else {
+                    {
+                        uint32_t r0[16];
+                        tmem_ld_x16(tmem + lane_base + acc * C::kAccBufCols + c0, r0);
+                        tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
+                    }
+                    if (lead && last_seg && c0 == 0) trace_stamp(args, 14);
+#pragma unroll
+                    for (int ch = 1; ch < C::kChains; ++ch) {
+                        uint32_t r1[16];
+                        tmem_ld_x16(tmem + lane_base + acc * C::kAccBufCols + ch * NTOK + c0, r1);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
+                    }
                 }
                 if (is_contrib) {
 #pragma unroll
@@ -822,7 +857,19 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         for (int j = 0; j < 16; ++j) v[j] += x[j];
                     }
                 }
-                if (!PETIT_DBG(args.debug_flags, 64u)) {
+                if (PETIT_DIRECT_STORE16 && NTOK == 16) {
+                    // one 16-token group per tile: fire-and-forget 2-byte stores (a warp covers
+                    // 64 contiguous bytes per token) instead of staging + TMA store + the wait
+                    // for the store to have read shared memory before the CTA may exit
+                    uint16_t *cp = static_cast<uint16_t *>(args.c) + (size_t)(m0 + c0) * args.n +
+                                   (size_t)g.n_tile * kTileN + row;
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if ((uint32_t)(c0 + j) < m_valid)
+                                cp[(size_t)j * args.n] = to_bits16<C::kIsBf16>(v[j] * gs);
+                    }
+                } else if (!PETIT_DBG(args.debug_flags, 64u)) {
                     // [16 tokens][128 rows] 16-bit staging tile -> one TMA store; the tensor
                     // map clips tokens >= M and rows >= N.  Three buffers in rotation: the
                     // wait below (before the barrier) leaves only the previous group's store

@@ -14,7 +14,6 @@
 #include "layout.cuh"
 #include "repack.h"
 
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -31,9 +30,6 @@ constexpr uint64_t kElemNv = 1, kElemMx = 2;
 constexpr uint64_t kMfmaF16 = 0, kMfmaBf16 = 1;
 constexpr int kTokVariants[] = {16, 32, 64, 128, 256};
 constexpr int kNumVariants = 5;
-
-// stream-K tail ramp default (PETIT_RAMP overrides; 0 = equal ranges)
-constexpr unsigned kDefaultRampN = 0, kDefaultRampD = 0;
 
 constexpr int stage_k_for(int ntok) { return ntok <= 64 ? 256 : (ntok == 128 ? 128 : 64); }
 
@@ -226,16 +222,6 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
             return e ? std::atoi(e) : 0;
         }();
         args.skew_cycles = (uint32_t)skew;
-        // PETIT_RAMP="R,D": see Sched in fp4_gemm.cu (0 < R <= 32, D <= 16 units)
-        static const std::pair<unsigned, unsigned> ramp = [] {
-            unsigned r = 0, d = 0;
-            const char *e = std::getenv("PETIT_RAMP");
-            if (e && std::sscanf(e, "%u,%u", &r, &d) == 2 && r <= 32 && d <= 16 && d != 0)
-                return std::make_pair(r, d);
-            return std::make_pair(kDefaultRampN, kDefaultRampD);
-        }();
-        args.ramp_n = ramp.first;
-        args.ramp_d = ramp.second;
     }
     const int mode = d.elem_b == kElemMx
                          ? gemm::kModeMxBf16

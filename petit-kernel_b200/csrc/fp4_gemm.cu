@@ -23,9 +23,9 @@
 //    contiguous range per SM, so all 148 SMs stream the same number of bytes
 //    whatever the shape.  Tiles cut by a range boundary are reduced through an
 //    fp32 workspace by the last CTA to arrive, in a fixed order (bit-reproducible).
-//  * warp roles: 1 TMA producer, 1 MMA issuer, 16 dequant warps, 4 epilogue
-//    warps; accumulators are double-buffered in TMEM so the epilogue overlaps
-//    the next tile.
+//  * warp roles: 2 TMA producers (weights / token tiles), 1 MMA issuer, 16 dequant
+//    warps, 4 epilogue warps; accumulators are double-buffered in TMEM so the
+//    epilogue overlaps the next tile.
 #include "fp4_gemm.h"
 #include "dequant.cuh"
 #include "layout.cuh"
@@ -46,22 +46,6 @@ using namespace petit::dq;
 #endif
 #ifndef PETIT_DECODE_GROUPS_NVBF16
 #define PETIT_DECODE_GROUPS_NVBF16 1
-#endif
-// A/B switches for tools/build_variant.sh (defaults = the shipped configuration)
-#ifndef PETIT_REDUCER_PAIR
-#define PETIT_REDUCER_PAIR 1 // reducer loads two contributors' partials per L2 round trip
-#endif
-#ifndef PETIT_LDTM_PAIR
-#define PETIT_LDTM_PAIR 0 // epilogue reads two accumulator chains per tcgen05.wait::ld
-#endif
-#ifndef PETIT_DIRECT_STORE16
-#define PETIT_DIRECT_STORE16 0 // 16-token tiles: store C straight from registers (no smem staging / TMA)
-#endif
-#ifndef PETIT_PRIME_STAGES
-#define PETIT_PRIME_STAGES 0 // >0: the weight stream pauses after this many stages until the first token tile is requested
-#endif
-#ifndef PETIT_EPILOGUE_REGS88
-#define PETIT_EPILOGUE_REGS88 1 // epilogue warps take the 8 registers/thread the pool has left
 #endif
 
 namespace {
@@ -138,7 +122,8 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     // Decode tiles (NTOK <= 64), fp16 and MXFP4 only: two groups of 8 warps take
     // alternate 256-k stages, 4 chunks per thread, which halves the per-stage
     // bookkeeping per weight (measured gate_up M=16: fp16 76 -> 71 us, MXFP4 77 -> 65 us;
-    // NVFP4-bf16 gets no faster and spills at the 88-register cap, so it keeps 1 group).
+    // NVFP4-bf16 is no faster with two groups -- 57.9 vs 58.0 us, -DPETIT_DECODE_GROUPS_NVBF16=2,
+    // profiles/r01_variants_ab.log -- so it keeps 1 group).
     static constexpr int kGroups =
         kUsedSlices > kChunks ? kUsedSlices / kChunks
                               : (NTOK <= 64 ? (MODE != kModeNvBf16 ? PETIT_DECODE_GROUPS
@@ -170,7 +155,6 @@ struct Barriers {
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
     uint64_t part_full;     // reducer: partial tiles landed in the (drained) stage ring
-    uint64_t act_started;   // the first token tile has been requested (PETIT_PRIME_STAGES)
     uint32_t tmem_base;
     uint32_t flag;
 };
@@ -182,30 +166,13 @@ struct Sched {
     uint32_t total_units; // < 2^31, checked by the launcher
     uint32_t grid;
     uint32_t n_mul, n_add; // this CTA's n-tile = n_mul * (tile / m_tiles) + n_add
-    // Tail ramp (tuning knob PETIT_RAMP="R,D", default off): the last R CTAs get
-    // D*1/R .. D*R/R units less than the others.  The hardware hands out CTAs in blockIdx
-    // order as SMs free up behind the previous kernel on the stream, so the highest ids
-    // become resident last and cannot prefetch (profiles/r01_percta_summary.txt).
-    uint32_t ramp_n, ramp_d, ramp_sum; // ramp_sum = sum of all deficits
 
-    __device__ __forceinline__ uint32_t ramp_cum(uint32_t b) const { // deficits of CTAs < b
-        uint32_t c = 0;
-        for (uint32_t i = 1; i + (grid - ramp_n) <= b; ++i) c += ramp_d * i / ramp_n;
-        return c;
-    }
     __device__ __forceinline__ uint32_t begin(uint32_t b) const {
-        if (ramp_n == 0) return (uint32_t)((uint64_t)total_units * b / grid);
-        return (uint32_t)(((uint64_t)total_units + ramp_sum) * b / grid) - ramp_cum(b);
+        return (uint32_t)((uint64_t)total_units * b / grid);
     }
     // CTA that owns unit u (inverse of begin()).
     __device__ __forceinline__ uint32_t owner(uint32_t u) const {
-        if (ramp_n == 0) return (uint32_t)((((uint64_t)u + 1) * grid - 1) / total_units);
-        uint32_t lo = 0, hi = grid - 1; // smallest b with begin(b + 1) > u
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) / 2;
-            if (begin(mid + 1) > u) hi = mid; else lo = mid + 1;
-        }
-        return lo;
+        return (uint32_t)((((uint64_t)u + 1) * grid - 1) / total_units);
     }
 };
 
@@ -364,15 +331,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
     sched.grid = CL ? gridDim.x / 2 : gridDim.x;
     sched.n_mul = CL ? 2 : 1;
     sched.n_add = cta_rank;
-    // decode tiles only, and only with enough units per CTA that the ramp stays a small
-    // correction (every range keeps at least half of the average)
-    sched.ramp_n = sched.ramp_d = sched.ramp_sum = 0;
-    if (NTOK <= 64 && args.ramp_n != 0 && args.ramp_n < sched.grid &&
-        sched.total_units >= 2 * args.ramp_d * sched.grid) {
-        sched.ramp_n = args.ramp_n;
-        sched.ramp_d = args.ramp_d;
-        for (uint32_t i = 1; i <= args.ramp_n; ++i) sched.ramp_sum += args.ramp_d * i / args.ramp_n;
-    }
     const uint32_t u_begin = sched.begin(sched_id);
     const uint32_t u_end = sched.begin(sched_id + 1);
 
@@ -394,7 +352,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             mbar_init(&bars->acc_empty[i], kNumEpilogueWarps * C::kEpiTeams);
         }
         mbar_init(&bars->part_full, 1);
-        mbar_init(&bars->act_started, 1);
         fence_mbar_init();
     }
     if (warp == kMmaWarp) tmem_alloc(&bars->tmem_base, 512);
@@ -458,11 +415,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 const uint32_t ph = (it / C::kStages) & 1;
                 if (it >= (uint32_t)C::kStages)
                     mbar_wait(do_w ? &bars->empty[s] : &bars->empty_act[s], ph ^ 1);
-                // A CTA that becomes resident just before the dependency resolves would
-                // otherwise have a ring-full of weight copies queued in front of its first
-                // token tile.
-                if (PETIT_PRIME_STAGES > 0 && do_w && it == (uint32_t)PETIT_PRIME_STAGES)
-                    mbar_wait(&bars->act_started, 0);
                 if (elect_one()) {
                     uint8_t *st = stage_base + (size_t)s * C::kStageBytes;
                     trace_stage(args, it, do_w ? 0 : 1);
@@ -499,7 +451,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         } else
                             tma_load_3d(st, &tmap_act, &bars->full_act[s], 0, g.m_tile * NTOK,
                                         k_slab);
-                        if (PETIT_PRIME_STAGES > 0 && it == 0) mbar_arrive(&bars->act_started);
                     }
                 }
                 __syncwarp();
@@ -699,10 +650,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             if (is_reducer) b_last = sched.owner(g.tile * sched.k_tiles + sched.k_tiles - 1);
             const uint32_t out_tile = g.n_tile * sched.m_tiles + g.m_tile;
 
-            // Reducer: the other contributors published long ago, so their partials
-            // for the first 16 tokens are summed (in CTA order) into registers while
-            // the MMAs of this last segment are still running; the tail after
-            // acc_full is then just TMEM read + add + store.
+            // Reducer: contributors that met the tile at the start of their range published
+            // long ago, so their partials for the first 16 tokens are summed (in CTA order)
+            // into this thread's shared-memory slots while the MMAs of this last segment are
+            // still running; the tail after acc_full is then TMEM read + add + store.
             const uint32_t pre_addr = pre_smem + row * 4; // + j * 512: this thread's 16 sums
             // A tile split over many CTAs (small TP shards: 10 n-tiles on 148 SMs) would cost
             // one L2 round trip per contributor in the register path below; from 4
@@ -729,11 +680,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 // the first add; the sum order stays CTA order.  (A reducer whose last
                 // contributor publishes at the very end has these L2 round trips on the
                 // kernel's critical path: profiles/r01_percta_summary.txt, `down`.)
-                for (uint32_t b = b_first + 1; b <= b_last && ring_from != 0 && team == 0;
-                     b += PETIT_REDUCER_PAIR ? 2 : 1) {
+                for (uint32_t b = b_first + 1; b <= b_last && ring_from != 0 && team == 0; b += 2) {
                     const float *p = args.ws_partials +
                                      (size_t)(b * sched.n_mul + sched.n_add) * (kTileN * NTOK) + row;
-                    const bool two = PETIT_REDUCER_PAIR && b + 1 <= b_last;
+                    const bool two = b + 1 <= b_last;
                     const float *p2 = p + (size_t)sched.n_mul * (kTileN * NTOK);
                     float x[16], y[16];
 #pragma unroll
@@ -779,39 +729,21 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             for (int c0 = (int)team * 16; c0 < NTOK; c0 += 16 * C::kEpiTeams) {
                 if ((uint32_t)c0 >= m_valid) break; // tokens beyond M are never stored
                 float v[16];
-                if (PETIT_LDTM_PAIR && C::kChains >= 2) {
-                    // two accumulator chains per TMEM round trip; same sum order as below
-                    const uint32_t t0 = tmem + lane_base + acc * C::kAccBufCols + c0;
+                {
+                    uint32_t r0[16];
+                    tmem_ld_x16(tmem + lane_base + acc * C::kAccBufCols + c0, r0);
+                    tmem_wait_ld();
 #pragma unroll
-                    for (int ch = 0; ch < C::kChains; ch += 2) {
-                        uint32_t r0[16], r1[16];
-                        tmem_ld_x16(t0 + ch * NTOK, r0);
-                        tmem_ld_x16(t0 + (ch + 1) * NTOK, r1);
-                        tmem_wait_ld();
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
+                }
+                if (lead && last_seg && c0 == 0) trace_stamp(args, 14);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            v[j] = ch == 0 ? __uint_as_float(r0[j]) : v[j] + __uint_as_float(r0[j]);
-                            v[j] += __uint_as_float(r1[j]);
-                        }
-                    }
-                    if (lead && last_seg && c0 == 0) trace_stamp(args, 14);
-                } else {
-                    {
-                        uint32_t r0[16];
-                        tmem_ld_x16(tmem + lane_base + acc * C::kAccBufCols + c0, r0);
-                        tmem_wait_ld();
+                for (int ch = 1; ch < C::kChains; ++ch) {
+                    uint32_t r1[16];
+                    tmem_ld_x16(tmem + lane_base + acc * C::kAccBufCols + ch * NTOK + c0, r1);
+                    tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
-                    }
-                    if (lead && last_seg && c0 == 0) trace_stamp(args, 14);
-#pragma unroll
-                    for (int ch = 1; ch < C::kChains; ++ch) {
-                        uint32_t r1[16];
-                        tmem_ld_x16(tmem + lane_base + acc * C::kAccBufCols + ch * NTOK + c0, r1);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
-                    }
+                    for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
                 }
                 if (is_contrib) {
 #pragma unroll
@@ -857,19 +789,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         for (int j = 0; j < 16; ++j) v[j] += x[j];
                     }
                 }
-                if (PETIT_DIRECT_STORE16 && NTOK == 16) {
-                    // one 16-token group per tile: fire-and-forget 2-byte stores (a warp covers
-                    // 64 contiguous bytes per token) instead of staging + TMA store + the wait
-                    // for the store to have read shared memory before the CTA may exit
-                    uint16_t *cp = static_cast<uint16_t *>(args.c) + (size_t)(m0 + c0) * args.n +
-                                   (size_t)g.n_tile * kTileN + row;
-                    if (row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if ((uint32_t)(c0 + j) < m_valid)
-                                cp[(size_t)j * args.n] = to_bits16<C::kIsBf16>(v[j] * gs);
-                    }
-                } else if (!PETIT_DBG(args.debug_flags, 64u)) {
+                if (!PETIT_DBG(args.debug_flags, 64u)) {
                     // [16 tokens][128 rows] 16-bit staging tile -> one TMA store; the tensor
                     // map clips tokens >= M and rows >= N.  Three buffers in rotation: the
                     // wait below (before the barrier) leaves only the previous group's store

@@ -26,7 +26,6 @@ struct GemmArgs {
     uint32_t use_cluster;   // allow the 2-CTA multicast variant for 128/256-token tiles
     uint32_t use_pdl;       // launch with programmatic stream serialisation
     uint32_t skew_cycles;   // initial phase skew between k-slice warps (tuning knob)
-    uint32_t ramp_n, ramp_d; // stream-K tail ramp: the last ramp_n CTAs get up to ramp_d units less
     unsigned long long *trace; // optional [grid][16] globaltimer stamps (debug), else null
 };
 

@@ -47,9 +47,6 @@ using namespace petit::dq;
 #ifndef PETIT_DECODE_GROUPS_NVBF16
 #define PETIT_DECODE_GROUPS_NVBF16 1
 #endif
-#ifndef PETIT_LATE_POLL
-#define PETIT_LATE_POLL 0 // experiment (tools/build_variant.sh): see kLatePoll in the epilogue
-#endif
 
 namespace {
 
@@ -665,13 +662,24 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             const uint32_t ring_from = (is_reducer && b_last - b_first > 3u && b_last - b_first <= kRingFit) ? 0u : 16u;
             const bool last_seg = u + (g.kt1 - g.kt0) >= u_end;
             if (lead && last_seg) trace_stamp(args, 11);
-            // Sum of the contributors' partials for the first 16 tokens -> this thread's slots.
-            // Two contributors per round trip: all loads of a pair are in flight before the
-            // first add; the sum order stays CTA order.  (A reducer whose last contributor
-            // publishes at the very end has these L2 round trips on the kernel's critical
-            // path: profiles/r01_percta_summary.txt, `down`.)
-            auto load_partials = [&]() {
+            if (is_reducer) {
+                if (lead) {
+                    const uint32_t need = b_last - b_first;
+                    uint32_t seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
+                                     : "=r"(seen)
+                                     : "l"(args.ws_counters + out_tile)
+                                     : "memory");
+                    } while (seen < need);
+                    if (last_seg) trace_stamp(args, 12);
+                }
+                named_bar_sync(kEpilogueBarId, kAllEpiThreads);
 #pragma unroll 1
+                // Two contributors per round trip: all loads of a pair are in flight before
+                // the first add; the sum order stays CTA order.  (A reducer whose last
+                // contributor publishes at the very end has these L2 round trips on the
+                // kernel's critical path: profiles/r01_percta_summary.txt, `down`.)
                 for (uint32_t b = b_first + 1; b <= b_last && ring_from != 0 && team == 0; b += 2) {
                     const float *p = args.ws_partials +
                                      (size_t)(b * sched.n_mul + sched.n_add) * (kTileN * NTOK) + row;
@@ -693,36 +701,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         sts_f32(pre_addr + j * (kTileN * 4), acc);
                     }
                 }
-            };
-            // 16-token tiles (PETIT_LATE_POLL): if this CTA's own accumulator completes before
-            // the last contributor has published, the reducer does not sit in the poll loop:
-            // it reads and sums its accumulator chains first and only then waits for the
-            // counter, which takes the TMEM reads off the critical path behind the hand-shake.
-            // The result does not depend on the path taken (same sums in the same order).
-            constexpr bool kLatePoll = PETIT_LATE_POLL && NTOK == 16;
-            bool partials_ready = true;
-            if (is_reducer) {
-                if (lead) {
-                    const uint32_t need = b_last - b_first;
-                    uint32_t seen, got = 1;
-                    for (;;) {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
-                                     : "=r"(seen)
-                                     : "l"(args.ws_counters + out_tile)
-                                     : "memory");
-                        if (seen >= need) break;
-                        if (kLatePoll && ring_from != 0 &&
-                            mbar_try_wait(&bars->acc_full[acc], acc_ph)) {
-                            got = 0;
-                            break;
-                        }
-                    }
-                    if (kLatePoll) *reinterpret_cast<volatile uint32_t *>(&bars->flag) = got;
-                    if (last_seg) trace_stamp(args, 12);
-                }
-                named_bar_sync(kEpilogueBarId, kAllEpiThreads);
-                if (kLatePoll) partials_ready = *reinterpret_cast<volatile uint32_t *>(&bars->flag) != 0;
-                if (partials_ready) load_partials();
             }
             if (lead && last_seg) trace_stamp(args, 13);
             while (!mbar_try_wait(&bars->acc_full[acc], acc_ph)) __nanosleep(32);
@@ -773,22 +751,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         if ((uint32_t)(c0 + j) < m_valid)
                             __stcg(&slot[(size_t)(c0 + j) * kTileN + row], v[j]);
                     continue;
-                }
-                if (kLatePoll && is_reducer && !partials_ready) {
-                    // own sums are in registers; now wait for the last contributor
-                    if (lead) {
-                        const uint32_t need = b_last - b_first;
-                        uint32_t seen;
-                        do {
-                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
-                                         : "=r"(seen)
-                                         : "l"(args.ws_counters + out_tile)
-                                         : "memory");
-                        } while (seen < need);
-                    }
-                    named_bar_sync(kEpilogueBarId, kAllEpiThreads);
-                    load_partials();
-                    partials_ready = true;
                 }
                 if (is_reducer && (uint32_t)c0 < ring_from) {
 #pragma unroll

@@ -7,6 +7,9 @@
  *   petit_gemm_nvfp4_a16        <- fp4::GemmFp4Fp16Grid      lib/gemm/rocm/quantization/gemm.h:120-124
  *   petit_gemm_mxfp4_a16        <- fp4::GemmMxFp4Fp16Grid    gemm.h:126-130
  *   petit_get_solutions         <- fp4::GemmGetSolutions     gemm.h:132-133
+ *   petit_get_default_solution  <- fp4::ChooseDefaultFp4Fp16Solution  fp4/algo_chooser.cc:64-132
+ *   petit_tune_table_*          (feeds `bench_matmul -algo tune` results, tools/benchmarks/matmul/main.cc:269-325,
+ *                                back to the default chooser; no reference equivalent)
  *   petit_repack_fp4_weights    <- fp4::RepackNvFp4ToPetitFp4Weights  gemm.h:135-137
  *   petit_repack_nvfp4_scales   <- fp4::RepackNvFp4ToPetitFp4Scales   gemm.h:139-141
  *   petit_repack_mxfp4_scales   <- fp4::RepackMxFp4ToPetitFp4Scales   gemm.h:143-145
@@ -109,6 +112,31 @@ int petit_gemm_mxfp4_a16(void *c, const void *a, const void *b, const void *scal
  * solutions on return.  The values are SolutionId::Repr()-style 64-bit ids. */
 int petit_get_solutions(const PetitSolutionHints *hints, unsigned m, unsigned n, unsigned k,
                         uint64_t *sols, unsigned *n_sols);
+
+/* The solution a GEMM call with solution_id == PETIT_SOLUTION_AUTO uses for this problem: the
+ * tuned-solution table first, then the built-in rule (the role of
+ * ChooseDefaultFp4Fp16Solution, fp4/algo_chooser.cc:64-132).  Pure host code; returns 0,
+ * PETIT_ERROR_PROBLEM_SHAPE for shapes/types no kernel takes, -1 for an unsupported b_type. */
+int petit_get_default_solution(const PetitSolutionHints *hints, unsigned m, unsigned n,
+                               unsigned k, uint64_t *solution_id);
+
+/* Tuned-solution table (what `bench_matmul -algo tune` finds, fed
+ * back to the default chooser; the reference's README tells users to autotune but gives the
+ * result nowhere to live).  An entry applies to an exact (a_type, b_type, m, n, k).
+ *   petit_tune_table_set    add / replace one entry; solution_id must come from
+ *                           petit_get_solutions for the same hints (else
+ *                           PETIT_ERROR_KERNEL_SHAPE); PETIT_SOLUTION_AUTO removes the entry
+ *   petit_tune_table_load   text file, one entry per line:
+ *                           "<nvfp4|mxfp4> <bf16|fp16> <m> <n> <k> <16 hex digits>" (the id as
+ *                           bench_matmul prints it: its 8 bytes, little endian); '#' starts a
+ *                           comment.  Returns the number of entries read, -1 if the file
+ *                           cannot be read or a line is malformed (nothing is added then).
+ *   petit_tune_table_clear  forget everything (also what was loaded from $PETIT_TUNE_TABLE,
+ *                           which is read once, before the first lookup). */
+int petit_tune_table_set(const PetitSolutionHints *hints, unsigned m, unsigned n, unsigned k,
+                         uint64_t solution_id);
+int petit_tune_table_load(const char *path);
+void petit_tune_table_clear(void);
 
 /* in: u32 [out_chan, in_chan/8] row-major, nibble i of a word = element 8w+i;
  * out: in_chan*out_chan/2 bytes in the packed tile layout. */

@@ -14,11 +14,15 @@
 #include "layout.cuh"
 #include "repack.h"
 
+#include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <utility>
+#include <vector>
 
 namespace {
 
@@ -85,6 +89,85 @@ int default_ntok(unsigned m, unsigned n, unsigned k) {
 
 bool problem_shape_ok(unsigned n, unsigned k) {
     return n % 16 == 0 && k % layout::kTileK == 0;
+}
+
+// ---- tuned-solution table (petit_tune_table_*) --------------------------------
+// key: (is_mx, a_type, m, n, k) -> solution id
+using TuneKey = std::tuple<int, int, unsigned, unsigned, unsigned>;
+std::mutex g_tune_mu;
+std::map<TuneKey, uint64_t> g_tune;
+std::atomic<bool> g_tune_nonempty{false};
+std::once_flag g_tune_env_once;
+
+bool hints_types_ok(const PetitSolutionHints *h, bool is_mx) {
+    if (h->a_type != PETIT_DTYPE_FP16 && h->a_type != PETIT_DTYPE_BF16) return false;
+    return !is_mx || h->a_type == PETIT_DTYPE_BF16;
+}
+
+// true if `id` is a solution petit_get_solutions lists for these types
+bool solution_matches(uint64_t id, bool is_mx, int a_type) {
+    Decoded d;
+    if (!decode_solution(id, &d)) return false;
+    if ((d.elem_b == kElemMx) != is_mx) return false;
+    return (d.mfma == kMfmaBf16) == (a_type == PETIT_DTYPE_BF16);
+}
+
+int tune_load_file(const char *path) {
+    std::FILE *f = std::fopen(path, "r");
+    if (!f) return -1;
+    std::vector<std::pair<TuneKey, uint64_t>> parsed;
+    char line[256];
+    bool ok = true;
+    while (ok && std::fgets(line, sizeof line, f)) {
+        if (char *hash = std::strchr(line, '#')) *hash = 0;
+        char bt[16], at[16], hex[32];
+        unsigned m, n, k;
+        const int got = std::sscanf(line, "%15s %15s %u %u %u %31s", bt, at, &m, &n, &k, hex);
+        if (got <= 0) continue; // blank / comment-only line
+        const bool is_mx = !std::strcmp(bt, "mxfp4");
+        const int a_type = !std::strcmp(at, "bf16") ? PETIT_DTYPE_BF16
+                           : !std::strcmp(at, "fp16") ? PETIT_DTYPE_FP16 : -1;
+        ok = got == 6 && (is_mx || !std::strcmp(bt, "nvfp4")) && a_type >= 0 &&
+             std::strlen(hex) == 16;
+        uint64_t id = 0;
+        for (int b = 0; ok && b < 8; ++b) { // the id's 8 bytes, little endian
+            unsigned byte = 0;
+            ok = std::sscanf(hex + 2 * b, "%2x", &byte) == 1;
+            id |= (uint64_t)byte << (8 * b);
+        }
+        ok = ok && solution_matches(id, is_mx, a_type);
+        if (ok) parsed.push_back({TuneKey{is_mx, a_type, m, n, k}, id});
+    }
+    std::fclose(f);
+    if (!ok) return -1;
+    std::lock_guard<std::mutex> lock(g_tune_mu);
+    for (auto &e : parsed) g_tune[e.first] = e.second;
+    g_tune_nonempty = !g_tune.empty();
+    return (int)parsed.size();
+}
+
+// 0 if no entry (or the table is empty: one relaxed load on the hot path)
+uint64_t tune_lookup(bool is_mx, int a_type, unsigned m, unsigned n, unsigned k) {
+    std::call_once(g_tune_env_once, [] {
+        if (const char *e = std::getenv("PETIT_TUNE_TABLE")) tune_load_file(e);
+    });
+    if (!g_tune_nonempty.load(std::memory_order_relaxed)) return 0;
+    std::lock_guard<std::mutex> lock(g_tune_mu);
+    auto it = g_tune.find(TuneKey{is_mx, a_type, m, n, k});
+    return it == g_tune.end() ? 0 : it->second;
+}
+
+// What PETIT_SOLUTION_AUTO resolves to (types and shape already validated).
+Decoded default_solution(bool is_mx, int a_type, unsigned m, unsigned n, unsigned k) {
+    Decoded d;
+    if (uint64_t id = tune_lookup(is_mx, a_type, m, n, k)) {
+        decode_solution(id, &d); // entries are validated when they are added
+        return d;
+    }
+    d.ntok = default_ntok(m, n, k);
+    d.elem_b = is_mx ? kElemMx : kElemNv;
+    d.mfma = a_type == PETIT_DTYPE_BF16 ? kMfmaBf16 : kMfmaF16;
+    return d;
 }
 
 // ---- per-(device, stream) stream-K workspace --------------------------------
@@ -156,9 +239,7 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
         if (!problem_shape_ok(n, k)) return PETIT_ERROR_PROBLEM_SHAPE;
         if (hints->a_type != PETIT_DTYPE_FP16 && hints->a_type != PETIT_DTYPE_BF16)
             return PETIT_ERROR_PROBLEM_SHAPE;
-        d.ntok = default_ntok(m, n, k);
-        d.elem_b = is_mx ? kElemMx : kElemNv;
-        d.mfma = hints->a_type == PETIT_DTYPE_BF16 ? kMfmaBf16 : kMfmaF16;
+        d = default_solution(is_mx, hints->a_type, m, n, k);
     } else {
         if (!decode_solution(solution_id, &d)) return PETIT_ERROR_KERNEL_SHAPE;
         if (force_mx) d.elem_b = kElemMx; // gemm_fp4_fp16_grid.cc:91-94
@@ -282,6 +363,47 @@ int petit_get_solutions(const PetitSolutionHints *hints, unsigned m, unsigned n,
     }
     *n_sols = count;
     return 0;
+}
+
+int petit_get_default_solution(const PetitSolutionHints *hints, unsigned m, unsigned n,
+                               unsigned k, uint64_t *solution_id) {
+    if (!hints || !solution_id) return -1;
+    if (hints->b_type != PETIT_DTYPE_FP4_E2M1 && hints->b_type != PETIT_DTYPE_MXFP4_E2M1)
+        return -1;
+    const bool is_mx = hints->b_type == PETIT_DTYPE_MXFP4_E2M1;
+    if (!hints_types_ok(hints, is_mx) || !problem_shape_ok(n, k) || m == 0 || n == 0 || k == 0)
+        return PETIT_ERROR_PROBLEM_SHAPE;
+    const Decoded d = default_solution(is_mx, hints->a_type, m, n, k);
+    *solution_id = make_solution(d.ntok, d.elem_b, d.mfma);
+    return PETIT_OK;
+}
+
+int petit_tune_table_set(const PetitSolutionHints *hints, unsigned m, unsigned n, unsigned k,
+                         uint64_t solution_id) {
+    if (!hints) return -1;
+    if (hints->b_type != PETIT_DTYPE_FP4_E2M1 && hints->b_type != PETIT_DTYPE_MXFP4_E2M1)
+        return -1;
+    const bool is_mx = hints->b_type == PETIT_DTYPE_MXFP4_E2M1;
+    if (!hints_types_ok(hints, is_mx)) return PETIT_ERROR_PROBLEM_SHAPE;
+    const TuneKey key{is_mx, hints->a_type, m, n, k};
+    std::lock_guard<std::mutex> lock(g_tune_mu);
+    if (solution_id == PETIT_SOLUTION_AUTO) {
+        g_tune.erase(key);
+    } else {
+        if (!solution_matches(solution_id, is_mx, hints->a_type)) return PETIT_ERROR_KERNEL_SHAPE;
+        g_tune[key] = solution_id;
+    }
+    g_tune_nonempty = !g_tune.empty();
+    return PETIT_OK;
+}
+
+int petit_tune_table_load(const char *path) { return path ? tune_load_file(path) : -1; }
+
+void petit_tune_table_clear(void) {
+    std::call_once(g_tune_env_once, [] {}); // a later lookup must not re-read $PETIT_TUNE_TABLE
+    std::lock_guard<std::mutex> lock(g_tune_mu);
+    g_tune.clear();
+    g_tune_nonempty = false;
 }
 
 int petit_repack_fp4_weights(uint32_t *out, const uint32_t *in, unsigned in_chan,

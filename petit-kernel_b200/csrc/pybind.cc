@@ -429,6 +429,40 @@ PYBIND11_MODULE(ops, m) {
     m.def("dequant_dense", &DequantDense, "Dense dequantisation hook", py::arg("w"),
           py::arg("scales"), py::arg("global_scale"), py::arg("out_dtype"), py::arg("size_n"),
           py::arg("size_k"), py::arg("mx"), py::arg("packed"));
+    // extras: the default chooser and its tuned-solution table (petit.h: petit_tune_table_*)
+    m.def(
+        "get_default_solution",
+        [](int64_t size_m, int64_t size_n, int64_t size_k, py::object a_type, bool mx) {
+            PetitSolutionHints hints;
+            hints.a_type = hints.c_type = dtype_code(a_type);
+            hints.b_type = mx ? PETIT_DTYPE_MXFP4_E2M1 : PETIT_DTYPE_FP4_E2M1;
+            hints.require_high_precision = 0;
+            uint64_t id = 0;
+            int rc = petit_get_default_solution(&hints, size_m, size_n, size_k, &id);
+            TORCH_CHECK(rc == 0, "no kernel for this problem (code ", rc, ")");
+            return id;
+        },
+        py::arg("size_m"), py::arg("size_n"), py::arg("size_k"), py::arg("a_type"),
+        py::arg("mx") = false);
+    m.def(
+        "tune_table_set",
+        [](int64_t size_m, int64_t size_n, int64_t size_k, py::object a_type, bool mx,
+           int64_t solution_id) {
+            PetitSolutionHints hints;
+            hints.a_type = hints.c_type = dtype_code(a_type);
+            hints.b_type = mx ? PETIT_DTYPE_MXFP4_E2M1 : PETIT_DTYPE_FP4_E2M1;
+            hints.require_high_precision = 0;
+            int rc = petit_tune_table_set(&hints, size_m, size_n, size_k, (uint64_t)solution_id);
+            TORCH_CHECK(rc == 0, "solution id does not belong to these types (code ", rc, ")");
+        },
+        py::arg("size_m"), py::arg("size_n"), py::arg("size_k"), py::arg("a_type"), py::arg("mx"),
+        py::arg("solution_id"));
+    m.def("tune_table_load", [](const std::string &path) {
+        int n = petit_tune_table_load(path.c_str());
+        TORCH_CHECK(n >= 0, "cannot read tune table ", path);
+        return n;
+    });
+    m.def("tune_table_clear", []() { petit_tune_table_clear(); });
     m.def("solution_name", [](uint64_t id) { return std::string(petit_solution_name(id)); });
     m.def("packed_layout_version", []() { return petit_packed_layout_version(); });
 }

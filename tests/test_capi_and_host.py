@@ -177,3 +177,155 @@ def test_bench_matmul_cli_flag_errors():
     assert r.returncode == 1 and "k % 256" in r.stderr
     r = subprocess.run([exe, "-atype", "bf16", "-ctype", "fp16"], capture_output=True, text=True)
     assert r.returncode == 1
+
+
+# ---- default chooser + tuned-solution table (petit.h: petit_get_default_solution, petit_tune_table_*)
+def default_solution(lib, hints, m, n, k):
+    out = ctypes.c_uint64(0)
+    rc = lib.petit_get_default_solution(ctypes.byref(hints), m, n, k, ctypes.byref(out))
+    return rc, out.value
+
+
+def tile_tokens(sol):
+    return (sol & 0xFF) * 16  # tile_m field of the SolutionId layout (gemm.h:33-105)
+
+
+def test_default_solution_rule_is_queryable_on_the_host(lib):
+    lib.petit_tune_table_clear()
+    h = Hints(BF16, FP4, BF16, 0)
+    expect = {1: 16, 16: 16, 17: 32, 33: 64, 64: 64, 65: 128, 128: 128, 512: 128, 1024: 256}
+    for m, ntok in expect.items():
+        rc, sol = default_solution(lib, h, m, 8192, 8192)
+        assert rc == 0 and tile_tokens(sol) == ntok, (m, ntok, hex(sol))
+        rc2, sols = solutions(lib, h, m, 8192, 8192)
+        assert sol in sols  # the default is one of the enumerated solutions
+    # error behaviour: unsupported b_type -> -1 (algo_chooser.cc:20-23); bad shape / types -> 1
+    assert default_solution(lib, Hints(BF16, INT4, BF16, 0), 16, 8192, 8192)[0] == -1
+    assert default_solution(lib, h, 16, 8192, 8192 + 128)[0] == 1
+    assert default_solution(lib, Hints(FP16, MXFP4, FP16, 0), 16, 8192, 8192)[0] == 1
+
+
+def test_tune_table_overrides_the_default_for_an_exact_problem(lib, tmp_path):
+    lib.petit_tune_table_set.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint,
+                                         ctypes.c_uint64]
+    lib.petit_tune_table_clear()
+    h = Hints(BF16, FP4, BF16, 0)
+    _, sols = solutions(lib, h, 16, 8192, 8192)
+    _, rule = default_solution(lib, h, 16, 8192, 8192)
+    pick = [s for s in sols if s != rule][1]
+    assert lib.petit_tune_table_set(ctypes.byref(h), 16, 8192, 8192, pick) == 0
+    assert default_solution(lib, h, 16, 8192, 8192)[1] == pick
+    # exact match only: other m, other activation type keep the rule
+    assert default_solution(lib, h, 8, 8192, 8192)[1] == rule
+    hf = Hints(FP16, FP4, FP16, 0)
+    assert tile_tokens(default_solution(lib, hf, 16, 8192, 8192)[1]) == 16
+    # an id of the wrong family is refused (bf16 id for fp16 activations; nvfp4 id for mxfp4)
+    assert lib.petit_tune_table_set(ctypes.byref(hf), 16, 8192, 8192, pick) == 2
+    assert lib.petit_tune_table_set(ctypes.byref(Hints(BF16, MXFP4, BF16, 0)), 16, 8192, 8192, pick) == 2
+    assert lib.petit_tune_table_set(ctypes.byref(h), 16, 8192, 8192, 0x1234) == 2
+    # PETIT_SOLUTION_AUTO removes the entry
+    assert lib.petit_tune_table_set(ctypes.byref(h), 16, 8192, 8192, 2**64 - 1) == 0
+    assert default_solution(lib, h, 16, 8192, 8192)[1] == rule
+
+    # file format = what `bench_matmul -algo tune -table` appends
+    hm = Hints(BF16, MXFP4, BF16, 0)
+    _, msols = solutions(lib, hm, 1024, 8192, 8192)
+    table = tmp_path / "tune.txt"
+    table.write_text("# comment\n"
+                     f"nvfp4 bf16 16 8192 8192 {pick.to_bytes(8, 'little').hex()}\n"
+                     "\n"
+                     f"mxfp4 bf16 1024 8192 8192 {msols[0].to_bytes(8, 'little').hex()}  # tok16\n")
+    assert lib.petit_tune_table_load(str(table).encode()) == 2
+    assert default_solution(lib, h, 16, 8192, 8192)[1] == pick
+    assert default_solution(lib, hm, 1024, 8192, 8192)[1] == msols[0]
+    # malformed line: nothing is added, -1
+    bad = tmp_path / "bad.txt"
+    bad.write_text(f"nvfp4 bf16 32 8192 8192 {pick.to_bytes(8, 'little').hex()}\nnvfp4 bf16 64 8192\n")
+    assert lib.petit_tune_table_load(str(bad).encode()) == -1
+    assert tile_tokens(default_solution(lib, h, 32, 8192, 8192)[1]) == 32
+    assert lib.petit_tune_table_load(b"/nonexistent/petit_table") == -1
+    lib.petit_tune_table_clear()
+    assert default_solution(lib, h, 16, 8192, 8192)[1] == rule
+
+
+def test_tune_table_env_is_read_once_in_a_fresh_process(tmp_path):
+    """PETIT_TUNE_TABLE=<file> is loaded before the first lookup (host-only query, no GPU)."""
+    code = (
+        "import ctypes, sys\n"
+        "lib = ctypes.CDLL(sys.argv[1])\n"
+        "class H(ctypes.Structure):\n"
+        "    _fields_ = [(n, ctypes.c_int32) for n in ('a', 'b', 'c', 'p')]\n"
+        "out = ctypes.c_uint64(0)\n"
+        "assert lib.petit_get_default_solution(ctypes.byref(H(5, 3, 5, 0)), 16, 4096, 4096, ctypes.byref(out)) == 0\n"
+        "print((out.value & 0xFF) * 16)\n")
+    lib_path = ensure_built()
+    plain = subprocess.run([os.sys.executable, "-c", code, lib_path], capture_output=True, text=True,
+                           env={k: v for k, v in os.environ.items() if k != "PETIT_TUNE_TABLE"})
+    assert plain.stdout.strip() == "16", plain.stderr
+    lib = ctypes.CDLL(lib_path)
+    _, sols = solutions(lib, Hints(BF16, FP4, BF16, 0), 16, 4096, 4096)
+    tok64 = [s for s in sols if tile_tokens(s) == 64][0]
+    table = tmp_path / "t.txt"
+    table.write_text(f"nvfp4 bf16 16 4096 4096 {tok64.to_bytes(8, 'little').hex()}\n")
+    tuned = subprocess.run([os.sys.executable, "-c", code, lib_path], capture_output=True, text=True,
+                           env=dict(os.environ, PETIT_TUNE_TABLE=str(table)))
+    assert tuned.stdout.strip() == "64", tuned.stderr
+
+
+# ---- framework glue (petit_kernel.petit_utils) and tuning helpers: host-side logic
+def test_petit_utils_support_checks_and_state_validation():
+    import petit_kernel.petit_utils as pu
+    from petit_kernel import ops
+
+    pu.verify_petit_nvfp4_supported("NVFP4", 16)
+    pu.verify_petit_nvfp4_supported("NVFP4", None)
+    pu.verify_petit_mxfp4_supported("MXFP4", 32)
+    with pytest.raises(ValueError, match="only supports: NVFP4"):
+        pu.verify_petit_nvfp4_supported("FP8", 16)
+    with pytest.raises(ValueError, match="group_size=16"):
+        pu.verify_petit_nvfp4_supported("NVFP4", 32)
+    with pytest.raises(ValueError, match="group_size=32"):
+        pu.verify_petit_mxfp4_supported("MXFP4", 16)
+
+    n, k = 64, 256
+    state = {"petit_format": "NVFP4", "petit_layout_version": ops.packed_layout_version(),
+             "size_n": n, "size_k": k,
+             "weight": torch.zeros(n // 16, 2 * k, dtype=torch.int32),
+             "weight_scale": torch.zeros(n, k // 16, dtype=torch.uint8)}
+    pu.check_packed_state(state, "NVFP4")
+    with pytest.raises(ValueError, match="expected 'MXFP4'"):
+        pu.check_packed_state(state, "MXFP4")
+    with pytest.raises(ValueError, match="layout version"):
+        pu.check_packed_state(dict(state, petit_layout_version=ops.packed_layout_version() - 1))
+    with pytest.raises(ValueError, match="weight size"):
+        pu.check_packed_state(dict(state, size_k=2 * k))
+    with pytest.raises(ValueError, match="scale size"):
+        pu.check_packed_state(dict(state, weight_scale=torch.zeros(n, k // 32, dtype=torch.uint8)))
+    with pytest.raises(ValueError, match="not been prepared"):
+        pu.export_packed_state(torch.nn.Module())
+    # the helpers keep the frameworks' signatures
+    assert list(inspect.signature(pu.apply_petit_nvfp4_linear).parameters) == [
+        "input", "weight", "weight_scale", "weight_scale_2", "size_n", "size_k", "bias"]
+    assert list(inspect.signature(pu.prepare_nvfp4_layer_for_petit).parameters) == ["layer"]
+
+
+def test_tuning_table_round_trip_through_python(tmp_path):
+    import petit_kernel.tuning as tuning
+    from petit_kernel import ops
+
+    tuning.clear_table()
+    sols = ops.get_fp4_solutions(16, 4096, 4096, torch.bfloat16, torch.bfloat16)
+    rule = tuning.default_solution(16, 4096, 4096, torch.bfloat16)
+    pick = [s for s in sols if s != rule][0]
+    tuning.set_solution(16, 4096, 4096, torch.bfloat16, False, pick)
+    assert tuning.default_solution(16, 4096, 4096, torch.bfloat16) == pick
+    path = tmp_path / "table.txt"
+    assert tuning.save_table(str(path)) == 1
+    assert f"nvfp4 bf16 16 4096 4096 {tuning.solution_hex(pick)}" in path.read_text()
+    tuning.clear_table()
+    assert tuning.default_solution(16, 4096, 4096, torch.bfloat16) == rule
+    assert tuning.load_table(str(path)) == 1
+    assert tuning.default_solution(16, 4096, 4096, torch.bfloat16) == pick
+    tuning.clear_table()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        tuning.tune_gemm(torch.zeros(1, 256), None, None, None, 1, 64, 256)

@@ -456,3 +456,101 @@ def test_peer_allreduce_two_gpus(pk):
                         "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
                         "29541", script], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "PEER_ALLREDUCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------ section 8f rows: glue + tuning
+class _FakeLinear(torch.nn.Module):
+    """What a framework's quantised linear layer looks like right after weight loading."""
+
+    def __init__(self, q_u8, scales, n, k):
+        super().__init__()
+        self.output_size_per_partition, self.input_size_per_partition = n, k
+        self.weight = torch.nn.Parameter(q_u8.cuda(), requires_grad=False)          # [N, K/2] u8
+        self.weight_scale = torch.nn.Parameter(scales.cuda(), requires_grad=False)  # e4m3 / e8m0
+
+
+@pytest.mark.parametrize("fmt", ["nvfp4", "mxfp4"])
+def test_framework_glue_prepare_apply_and_versioned_state(pk, fmt):
+    """petit_kernel.petit_utils: weight-load -> forward exactly as vLLM / SGLang drive the ops
+    (3-D activations, in-place bias add), then export / reload of the packed tensors."""
+    import petit_kernel.petit_utils as pu
+
+    n, k, seed = 384, 1024, 7
+    make = orc.make_nvfp4_case if fmt == "nvfp4" else orc.make_mxfp4_case
+    a, q, s, gs = make(2 * 5, n, k, seed)
+    layer = _FakeLinear(q, s, n, k)
+    prepare = pu.prepare_nvfp4_layer_for_petit if fmt == "nvfp4" else pu.prepare_mxfp4_layer_for_petit
+    apply = pu.apply_petit_nvfp4_linear if fmt == "nvfp4" else pu.apply_petit_mxfp4_linear
+    prepare(layer)
+    assert not layer.weight.requires_grad and layer.petit_layout_version == pk.ops.packed_layout_version()
+    assert tuple(layer.weight.shape) == (n // 16, 2 * k) and layer.weight.dtype == torch.int32
+
+    x = a.cuda().reshape(2, 5, k)
+    bias = torch.linspace(-1, 1, n, dtype=torch.bfloat16, device="cuda")
+    y = apply(x, layer.weight, layer.weight_scale, gs.cuda(), n, k, bias)
+    assert y.shape == (2, 5, n) and y.dtype == torch.bfloat16
+    w = orc.dequant_nvfp4(q.numpy(), s.view(torch.uint8).numpy()) if fmt == "nvfp4" \
+        else orc.dequant_mxfp4(q.numpy(), s.numpy())
+    ref = (a.float() @ torch.from_numpy(w).t()) * gs.item() + bias.float().cpu()
+    assert orc.max_rel_err(y.reshape(-1, n), ref) <= GEMM_TOL
+    y0 = apply(x, layer.weight, layer.weight_scale, gs.cuda(), n, k)  # no bias
+    assert orc.max_rel_err(y0.reshape(-1, n), ref - bias.float().cpu()) <= GEMM_TOL
+
+    state = pu.export_packed_state(layer)
+    other = torch.nn.Module()
+    pu.load_packed_state(other, {key: (v.clone() if torch.is_tensor(v) else v) for key, v in state.items()})
+    y1 = apply(x, other.weight, other.weight_scale, gs.cuda(), n, k, bias)
+    assert torch.equal(y1, y)
+    with pytest.raises(ValueError, match="layout version"):
+        pu.load_packed_state(torch.nn.Module(), dict(state, petit_layout_version=1))
+
+
+def test_tune_gemm_feeds_the_default_chooser(pk, tmp_path):
+    """petit_kernel.tuning.tune_gemm times every listed solution on the caller's tensors and
+    makes the fastest the default; solution_id=-1 then runs exactly that kernel."""
+    import petit_kernel.tuning as tuning
+
+    tuning.clear_table()
+    m, n, k = 48, 1024, 2048
+    a, q, s, gs = orc.make_nvfp4_case(m, n, k, 11)
+    b, sp = pack_nvfp4(pk, q, s, n, k)
+    a, gs = a.cuda(), gs.cuda()
+    res = tuning.tune_gemm(a, b, sp, gs, m, n, k, repeat=5)
+    assert len(res) == 5 and all(us > 0 for us, _ in res) and res == sorted(res)
+    best = res[0][1]
+    assert tuning.default_solution(m, n, k, torch.bfloat16) == best
+    c_auto = pk.mul_nvfp4_a16(a, b, sp, gs, m, n, k, -1)
+    c_best = pk.mul_nvfp4_a16(a, b, sp, gs, m, n, k, best)
+    assert torch.equal(c_auto, c_best)
+    ref = gpu_ref_f32(pk, a, b, sp, gs, n, k, False)
+    assert orc.max_rel_err(c_auto, ref.cpu()) <= GEMM_TOL
+    # a forced large-tile entry is honoured too (any tile is valid for any m)
+    tok256 = [sol for _, sol in res if (sol & 0xFF) * 16 == 256][0]
+    tuning.set_solution(m, n, k, torch.bfloat16, False, tok256)
+    assert pk.ops.solution_name(tuning.default_solution(m, n, k, torch.bfloat16)).endswith("tok256")
+    c_256 = pk.mul_nvfp4_a16(a, b, sp, gs, m, n, k, -1)
+    assert orc.max_rel_err(c_256, ref.cpu()) <= GEMM_TOL
+    path = tmp_path / "table.txt"
+    assert tuning.save_table(str(path)) == 1
+    tuning.clear_table()
+    assert tuning.default_solution(m, n, k, torch.bfloat16) != tok256
+
+
+def test_bench_matmul_cli_writes_a_loadable_table(pk, tmp_path):
+    import petit_kernel.tuning as tuning
+
+    exe = os.path.join(ROOT, "tools", "bench_matmul")
+    if not os.path.exists(exe):
+        pytest.skip("bench_matmul not built")
+    table = tmp_path / "tuned.txt"
+    r = subprocess.run([exe, "-m", "16", "-n", "1024", "-k", "1024", "-atype", "bf16", "-ctype", "bf16",
+                        "-btype", "mxfp4", "-warmup", "2", "-repeat", "5", "-algo", "tune",
+                        "-table", str(table)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    fields = table.read_text().split()
+    assert fields[:5] == ["mxfp4", "bf16", "16", "1024", "1024"] and len(fields[5]) == 16
+    tuning.clear_table()
+    assert tuning.load_table(str(table)) == 1
+    sol = tuning.default_solution(16, 1024, 1024, torch.bfloat16, mx=True)
+    assert tuning.solution_hex(sol) == fields[5]
+    tuning.clear_table()

@@ -6,7 +6,9 @@
 //   bench_matmul -m 16 -n 8192 -k 8192 -atype bf16 -ctype bf16 -btype nvfp4 -algo <hex id>
 //
 // -algo ""      default solution (PETIT_SOLUTION_AUTO)
-// -algo tune    time every solution petit_get_solutions lists, print the 5 fastest
+// -algo tune    time every solution petit_get_solutions lists, print the 5 fastest;
+//               with -table FILE also append "<btype> <atype> m n k <hex>" for the fastest one,
+//               the format PETIT_TUNE_TABLE / petit_tune_table_load feed to the default chooser
 // -algo <hex>   the 8 bytes of a solution id as printed by tune mode
 //
 // Differences from the reference, on purpose: time is measured with CUDA events on the
@@ -30,6 +32,7 @@ namespace {
 
 struct Flags {
     std::string backend = "petit", algo = "", atype = "fp16", ctype = "fp16", btype = "nvfp4";
+    std::string table; // -algo tune: append the fastest solution here (petit_tune_table_load format)
     int m = 128, n = 4096, k = 4096, batch = 1, warmup = 10, repeat = 100, copies = 0;
 };
 
@@ -61,6 +64,7 @@ bool parse_flags(int argc, char **argv, Flags *f) {
         else if (key == "warmup") f->warmup = std::atoi(v.c_str());
         else if (key == "repeat") f->repeat = std::atoi(v.c_str());
         else if (key == "copies") f->copies = std::atoi(v.c_str());
+        else if (key == "table") f->table = v;
         else {
             std::fprintf(stderr, "Unknown flag: -%s\n", key.c_str());
             return false;
@@ -163,7 +167,7 @@ int main(int argc, char **argv) {
         std::fprintf(stderr,
                      "usage: bench_matmul [-backend petit] -m M -n N -k K [-warmup W] [-repeat R] "
                      "[-algo ''|tune|<hex>] [-atype fp16|bf16] [-ctype fp16|bf16] "
-                     "[-btype nvfp4|mxfp4] [-batch 1] [-copies C]\n");
+                     "[-btype nvfp4|mxfp4] [-batch 1] [-copies C] [-table FILE]\n");
         return 1;
     }
     if (f.backend != "petit") {
@@ -273,6 +277,18 @@ int main(int argc, char **argv) {
         std::sort(results.begin(), results.end());
         for (size_t i = 0; i < results.size() && i < 5; ++i)
             p.print(hex_of(results[i].second), results[i].first);
+        if (!f.table.empty() && !results.empty()) {
+            // one line per tuned problem; PETIT_TUNE_TABLE=<file> / petit_tune_table_load feed
+            // it back to the default chooser
+            if (std::FILE *tf = std::fopen(f.table.c_str(), "a")) {
+                std::fprintf(tf, "%s %s %d %d %d %s\n", f.btype.c_str(), f.atype.c_str(), f.m, f.n,
+                             f.k, hex_of(results[0].second).c_str());
+                std::fclose(tf);
+            } else {
+                std::fprintf(stderr, "cannot append to %s\n", f.table.c_str());
+                return 2;
+            }
+        }
         return results.empty() ? 2 : 0;
     }
 

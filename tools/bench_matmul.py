@@ -3,7 +3,9 @@
 tools/benchmarks/matmul.py:92-195: the same default entries (M in {16, 256, 512} x the
 Llama-3 8B/70B projection shapes), the same flags (--backend/--atype/--btype/--ctype),
 `-algo tune` for every entry, stdout passed through.  Adds --csv to collect the best
-solution per entry (the reference leaves parsing to the reader)."""
+solution per entry (the reference leaves parsing to the reader) and --table to write them
+as a tuned-solution table: `PETIT_TUNE_TABLE=<file>` (or `petit_tune_table_load`) makes
+the library's default chooser use it."""
 import argparse
 import csv
 import os
@@ -25,6 +27,8 @@ def run_benchmark(m, n, k, args):
     cmd = [os.path.join(ROOT, "bench_matmul"), "-backend", args.backend, "-atype", args.atype,
            "-btype", args.btype, "-ctype", args.ctype, "-m", str(m), "-k", str(k), "-n", str(n),
            "-warmup", str(WARMUP), "-repeat", str(REPEAT), "-batch", str(BATCH), "-algo", ALGO]
+    if args.table:
+        cmd += ["-table", args.table]
     try:
         result = subprocess.run(cmd, capture_output=True, text=True, timeout=args.timeout)
     except Exception as exc:  # noqa: BLE001
@@ -49,6 +53,8 @@ def main():
     ap.add_argument("--btype", default="nvfp4")
     ap.add_argument("--ctype", default="fp16")
     ap.add_argument("--csv", default=None, help="write the best solution per entry here")
+    ap.add_argument("--table", default=None,
+                    help="append '<btype> <atype> m n k <hex id>' of the fastest solution per entry")
     ap.add_argument("--timeout", type=float, default=300.0)
     args = ap.parse_args()
     rows = [r for r in (run_benchmark(m, n, k, args) for m, n, k in ENTRIES) if r]

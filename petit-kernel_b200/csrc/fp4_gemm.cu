@@ -633,7 +633,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             const bool full_k = g.kt0 == 0 && g.kt1 == sched.k_tiles;
             const uint32_t m0 = g.m_tile * NTOK;
             const uint32_t m_valid = args.m - m0 < (uint32_t)NTOK ? args.m - m0 : NTOK;
-            const bool row_ok = row < rows;
 
             // Split tiles (stream-K): the CTA that owns the FIRST k-part of a tile
             // reaches it as the last segment of its range, after every other

@@ -47,16 +47,6 @@ using namespace petit::dq;
 #ifndef PETIT_DECODE_GROUPS_NVBF16
 #define PETIT_DECODE_GROUPS_NVBF16 1
 #endif
-// Experiment prepared from the per-instruction samples of profiles/r01_ncu_sass_samples_gate_up.txt,
-// NOT MEASURED YET (build with tools/build_variant.sh <name> . -DPETIT_PREFETCH_WAITS=1): 22 % of
-// the dequant warps' samples sit behind the two mbarrier.try_wait of a stage (full[s], then
-// a_empty[ta]) waiting for the predicate, although the barriers have almost always completed
-// -- it is the latency of the instruction, paid twice per stage, serially.  The variant issues
-// the two try_waits of the NEXT stage while the TMEM stores of the current one drain and
-// consumes the predicates at the top of the next iteration.
-#ifndef PETIT_PREFETCH_WAITS
-#define PETIT_PREFETCH_WAITS 0
-#endif
 
 namespace {
 
@@ -544,10 +534,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             while (clock64() - t0 < wait) {
             }
         }
-        // PETIT_PREFETCH_WAITS: predicates of the next stage's barriers, requested one stage ahead
-        constexpr bool kPrefetchWaits = PETIT_PREFETCH_WAITS && C::kGroups == 1;
-        const uint32_t total_stages = (u_end - u_begin) * C::kStagesPerUnit;
-        bool pref_valid = false, pref_full = false, pref_a_empty = false;
         for (uint32_t u = u_begin; u < u_end;) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t rows = tile_rows(args.n, g.n_tile);
@@ -566,15 +552,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     continue;
                 }
                 const uint32_t st = w_base + s * C::kStageBytes;
-                bool a_empty_ok = false;
-                if (kPrefetchWaits) {
-                    // both predicates in flight before the first one is consumed
-                    const bool full_ok = pref_valid ? pref_full : mbar_try_wait(&bars->full[s], ph);
-                    a_empty_ok = pref_valid ? pref_a_empty : mbar_try_wait(&bars->a_empty[ta], ta_ph);
-                    if (!full_ok) mbar_wait(&bars->full[s], ph);
-                } else {
-                    mbar_wait(&bars->full[s], ph);
-                }
+                mbar_wait(&bars->full[s], ph);
                 if (threadIdx.x == kFirstDequantWarp * 32) trace_stage(args, it_dbg, 2);
                 uint4 q[kMyChunks];
 #pragma unroll
@@ -591,7 +569,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         scw[p] = C::kIsMx ? lds_u8(a) : lds_u16(a);
                 }
                 // the previous occupant of this TMEM A stage must have been consumed
-                if (!kPrefetchWaits || !a_empty_ok) mbar_wait(&bars->a_empty[ta], ta_ph);
+                mbar_wait(&bars->a_empty[ta], ta_ph);
                 tc_fence_after();
                 if (threadIdx.x == kFirstDequantWarp * 32) trace_stage(args, it_dbg, 3);
 #pragma unroll
@@ -608,20 +586,6 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     dequant_chunk<MODE>(q[ci], mult, two_step, out);
                     if (!PETIT_DBG(args.debug_flags, 16u)) // experiment: no TMEM stores
                     tmem_st_x16(tmem_dst + ta * C::kACols + ci * 16, out);
-                }
-                if (kPrefetchWaits) {
-                    // Next stage's predicates, requested while this stage's TMEM stores drain.
-                    // This warp has consumed the previous phase of both barriers, so the
-                    // parity test cannot alias; nothing is requested past the CTA's last
-                    // stage (a try_wait on a phase that never completes returns only after
-                    // the hardware time limit).
-                    pref_valid = it_dbg + 1 < total_stages;
-                    if (pref_valid) {
-                        const uint32_t s1 = s + 1 == C::kStages ? 0 : s + 1;
-                        const uint32_t ta1 = ta + 1 == C::kAStages ? 0 : ta + 1;
-                        pref_full = mbar_try_wait(&bars->full[s1], s1 == 0 ? ph ^ 1 : ph);
-                        pref_a_empty = mbar_try_wait(&bars->a_empty[ta1], ta1 == 0 ? ta_ph ^ 1 : ta_ph);
-                    }
                 }
                 tmem_wait_st();
                 tc_fence_before();

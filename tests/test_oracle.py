@@ -127,3 +127,62 @@ def test_matcher_and_pm0_helpers():
     y = torch.tensor([-0.0, 1.5], dtype=torch.bfloat16)
     assert orc.bits_equal_pm0(x, y)
     assert not orc.bits_equal_pm0(x, torch.tensor([0.0, 1.25], dtype=torch.bfloat16))
+
+
+# ---- pinned to the reference's own C++ host code (oracle/_ref, tests/golden/make_golden_cpp.py)
+def _pm0_equal_bits16(a, b, nan_mask_bits):
+    """The reference's Element::operator== (lib/tests/floating_points.h:184-202): +0 == -0,
+    NaN never equal, otherwise bit equality."""
+    a, b = a.astype(np.uint16), b.astype(np.uint16)
+    both_zero = ((a & 0x7FFF) == 0) & ((b & 0x7FFF) == 0)
+    nan = ((a & 0x7FFF) > nan_mask_bits) | ((b & 0x7FFF) > nan_mask_bits)
+    return (both_zero | (a == b)) & ~nan
+
+
+def test_oracle_matches_reference_cpp_numeric_helpers():
+    """nvfp4_exhaustive_cpp.npz was produced by the reference's fp8_e4m3_t / bf16_t / fp16_t
+    (compiled from /root/reference); the Python oracle and the torch-made golden table agree
+    with it bit for bit, i.e. the oracle reproduces what ExhaustiveFp4DequantTest expects."""
+    g = golden("nvfp4_exhaustive_cpp.npz")
+    assert list(g["eq_pm0_nan_same"]) == [1, 0, 1]
+    # e4m3 -> fp32, all 256 bytes (NaN payloads are not compared)
+    ref = g["e4m3_f32_bits"].view(np.float32)
+    got = orc.e4m3_to_f32(np.arange(256, dtype=np.uint8))
+    assert np.array_equal(np.isnan(ref), np.isnan(got))
+    ok = ~np.isnan(ref)
+    assert np.array_equal(ref[ok].view(np.uint32), got[ok].view(np.uint32))
+    # scale * LUT in fp32: identical products, same table as the one made by the Python reference
+    sb = g["scale_bits"]
+    assert sb[0] == 0x01 and sb[-1] == 0x7E
+    expect = (orc.E2M1_VALUES[:, None] * orc.e4m3_to_f32(sb)[None, :]).astype(np.float32)
+    assert np.array_equal(expect.view(np.uint32), g["product_f32_bits"])
+    py = golden("nvfp4_exhaustive.npz")
+    assert np.array_equal(py["scale_bits"], sb)
+    assert np.array_equal(py["table"].view(np.uint32), g["product_f32_bits"])
+    # Element::from_fp32: round-to-nearest-even to bf16 / fp16 = torch's conversion; exact here
+    t = torch.from_numpy(expect.copy())
+    bf = t.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    fp = t.to(torch.float16).view(torch.int16).numpy().view(np.uint16)
+    assert _pm0_equal_bits16(bf, g["bf16_bits"], 0x7F80).all()
+    assert _pm0_equal_bits16(fp, g["fp16_bits"], 0x7C00).all()
+    assert np.array_equal(bf, g["bf16_bits"]) and np.array_equal(fp, g["fp16_bits"])
+
+
+def test_reference_cpp_driver_reproduces_the_committed_fixture():
+    """Where the reference checkout (and therefore oracle/_ref/ref_numeric) exists, the
+    committed fixture is exactly what the reference's code prints today."""
+    import os
+    import sys
+
+    from helpers import ROOT
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_numeric")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_cpp import run_reference_driver
+
+    live = run_reference_driver(exe)
+    g = golden("nvfp4_exhaustive_cpp.npz")
+    for key, val in live.items():
+        assert np.array_equal(val, g[key]), key

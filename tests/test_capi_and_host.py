@@ -329,3 +329,14 @@ def test_tuning_table_round_trip_through_python(tmp_path):
     tuning.clear_table()
     with pytest.raises(RuntimeError, match="no CPU path"):
         tuning.tune_gemm(torch.zeros(1, 256), None, None, None, 1, 64, 256)
+
+
+def test_percta_trace_tool_summarises_the_committed_traces():
+    """tools/analyze_percta.py (per-CTA two-launch traces -> percentiles and late CTAs) runs on
+    the committed CSV and reports every event of the four decode GEMMs."""
+    out = subprocess.run([os.sys.executable, os.path.join(ROOT, "tools", "analyze_percta.py"),
+                          os.path.join(ROOT, "profiles", "r01_percta_trace_70b_final.csv")],
+                         capture_output=True, text=True, check=True).stdout
+    for gemm in ("qkv", "o", "gate_up", "down"):
+        assert f"== {gemm} launch 1, 148 CTAs" in out
+    assert out.count("griddep_wait_done") == 4 and out.count("late cta") == 24

@@ -126,6 +126,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm uses all host cores at
+    # every N, so its value does not depend on how it was launched
+    torch.set_num_threads(os.cpu_count() or 1)
     shapes = [LAYER[1]]  # o_proj 8192 x 8192: bounded sample of the layer set
     steps = max(1, min(args.steps, 5))
     for _ in range(min(args.warmup, 1)):
@@ -268,6 +271,30 @@ def main():
         return outs
 
     args.allreduce_kind = allreduce_kind
+
+    # ---- TP outputs checked once before anything is timed: the row-parallel results of the
+    # data plane that is about to be measured against ncclAllReduce of the same partials
+    tp_check = None
+    if world > 1:
+        outs = layer_step(0)
+        parts = layer_step(0, collective=False)
+        max_abs, max_ref, identical = 0.0, 0.0, True
+        for (nm, n, k, kind, _, _), got, part in zip(layers[0], outs, parts):
+            if kind != "row":
+                continue
+            ref = part.clone()
+            dist.all_reduce(ref)
+            max_abs = max(max_abs, (got.float() - ref.float()).abs().max().item())
+            max_ref = max(max_ref, ref.float().abs().max().item())
+            gathered = [torch.empty_like(got) for _ in range(world)]
+            dist.all_gather(gathered, got.contiguous())
+            identical = identical and all(torch.equal(gathered[0], x) for x in gathered)
+        tp_check = {"vs": "ncclAllReduce of the same bf16 partials", "max_abs_diff": max_abs,
+                    "max_abs_ref": max_ref, "identical_across_ranks": identical,
+                    # NCCL rounds to bf16 per hop, the one-shot kernel once: one bf16 ulp of max
+                    "ok": bool(max_abs <= max_ref * 2 ** -6 and identical)}
+        if not tp_check["ok"]:
+            raise RuntimeError(f"TP output check failed: {tp_check}")
 
     def sync():
         if world > 1:
@@ -442,12 +469,17 @@ def main():
     shard_bytes = sum(algo_bytes(m, n, k) for _, n, k, _ in shard)
     avg_launch_us = sum(p["us"] for p in per_launch) / len(per_launch)
     achieved = (shard_bytes / len(shard)) / avg_launch_us * 1e-3
+    # dram__bytes_read+write per launch comes from an ncu capture of the unsharded layer set
+    # (profiles/): it only describes the N=1 workload
     traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")) as f:
-            traffic = json.load(f).get("avg_bytes_per_launch_m16")
-    except Exception:
-        pass
+    if world == 1:
+        for name in ("r02_dram_traffic.json", "r01_dram_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as f:
+                    traffic = json.load(f).get("avg_bytes_per_launch_m16")
+                break
+            except Exception:
+                pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
                 "peak_source": peak_src, "kernel": "fp4_gemm_kernel<nvfp4,bf16,tok16> (stream-K tcgen05)",
@@ -462,6 +494,7 @@ def main():
     if world == 1 and not args.no_details:
         details = sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak)
 
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1
     cores = torch.get_num_threads()
     t0 = time.perf_counter()
     cpu_gbs, cpu_s = cpu_reference_rate(m, [LAYER[1]], 2)
@@ -482,6 +515,8 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "frac_of_hbm_peak_layer_set": round(value / (hbm_peak * world), 4),
     }
+    if tp_check is not None:
+        out["tp_check"] = tp_check
     if details:
         out["details"] = details
     print(json.dumps(out))

@@ -184,13 +184,24 @@ int petit_hal_synchronize(void);
  * function); epoch is a local zero-initialised device buffer of
  * petit_allreduce_epoch_bytes().  Every rank must call it with the same numel, in the
  * same order per pad.  out must not alias the local buffer.  dtype: PETIT_DTYPE_BF16/FP16;
- * numel % 8 == 0; world <= 8.  end_barrier != 0: the local buffer may be overwritten as
- * soon as the call has completed on the stream; end_barrier == 0 (one NVLink round trip
- * less): only after the NEXT call of this group has completed, i.e. the caller alternates
- * between two buffers (each with its own pad and epoch).  A peer that never arrives traps
- * the kernel after ~4 s. */
+ * numel % 8 == 0; world <= 8.  `end_barrier` is a bit set:
+ *   PETIT_ALLREDUCE_END_BARRIER: the local buffer may be overwritten as soon as the call has
+ *     completed on the stream; without it (one NVLink round trip less) only after the NEXT
+ *     call of this group has completed, i.e. the caller alternates between two buffers
+ *     (each with its own pad and epoch) and issues at least one call on a buffer's pad
+ *     between a read of the buffer and its next overwrite (a CUDA graph that holds a single
+ *     call must therefore set the bit);
+ *   PETIT_ALLREDUCE_FENCED (or env PETIT_AR_FENCED=1): the peer flags use a
+ *     fence.acq_rel.sys release/acquire pattern instead of relaxed system-scope accesses
+ *     (+~4 us per barrier; see csrc/allreduce.cu for what the relaxed protocol relies on).
+ * A peer that does not arrive within PETIT_AR_TIMEOUT_MS (default 4000) makes the kernel
+ * give up without reducing; petit_allreduce_status (synchronises the stream) then returns
+ * 1 + the rank that was missing, 0 if every call so far completed, -1 on a CUDA error. */
+#define PETIT_ALLREDUCE_END_BARRIER 1
+#define PETIT_ALLREDUCE_FENCED 2
 size_t petit_allreduce_pad_bytes(void);
 size_t petit_allreduce_epoch_bytes(void);
+int petit_allreduce_status(const void *epoch, petit_stream_t stream);
 int petit_allreduce_oneshot(void *out, const void *const *peer_bufs, void *const *peer_pads,
                             void *epoch, int rank, int world, size_t numel, int dtype,
                             int end_barrier, petit_stream_t stream);

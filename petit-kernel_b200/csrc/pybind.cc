@@ -395,7 +395,7 @@ PYBIND11_MODULE(ops, m) {
         "allreduce_oneshot",
         [](const torch::Tensor &out, const std::vector<int64_t> &buf_ptrs,
            const std::vector<int64_t> &pad_ptrs, const torch::Tensor &epoch, int64_t rank,
-           int64_t numel, bool end_barrier) {
+           int64_t numel, bool end_barrier, bool fenced) {
             TORCH_CHECK(out.is_cuda() && out.is_contiguous(), "out must be a contiguous CUDA tensor");
             TORCH_CHECK(out.scalar_type() == torch::kBFloat16 || out.scalar_type() == torch::kHalf,
                         "out must be bf16 or fp16");
@@ -415,12 +415,18 @@ PYBIND11_MODULE(ops, m) {
                 out.data_ptr(), bufs, pads, epoch.data_ptr(), (int)rank, (int)buf_ptrs.size(),
                 (size_t)numel,
                 out.scalar_type() == torch::kBFloat16 ? PETIT_DTYPE_BF16 : PETIT_DTYPE_FP16,
-                end_barrier ? 1 : 0, at::cuda::getCurrentCUDAStream(out.device().index()).stream());
+                (end_barrier ? PETIT_ALLREDUCE_END_BARRIER : 0) | (fenced ? PETIT_ALLREDUCE_FENCED : 0),
+                at::cuda::getCurrentCUDAStream(out.device().index()).stream());
             TORCH_CHECK(rc == 0, "petit_allreduce_oneshot failed with code ", rc);
             return out;
         },
         py::arg("out"), py::arg("buf_ptrs"), py::arg("pad_ptrs"), py::arg("epoch"), py::arg("rank"),
-        py::arg("numel"), py::arg("end_barrier") = true);
+        py::arg("numel"), py::arg("end_barrier") = true, py::arg("fenced") = false);
+    m.def("allreduce_status", [](const torch::Tensor &epoch) {
+        c10::cuda::CUDAGuard guard(epoch.device());
+        return (int64_t)petit_allreduce_status(
+            epoch.data_ptr(), at::cuda::getCurrentCUDAStream(epoch.device().index()).stream());
+    });
     m.def("allreduce_pad_bytes", []() { return (int64_t)petit_allreduce_pad_bytes(); });
     m.def("allreduce_epoch_bytes", []() { return (int64_t)petit_allreduce_epoch_bytes(); });
 

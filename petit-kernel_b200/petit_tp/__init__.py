@@ -100,9 +100,17 @@ class PeerAllReduce:
     into a peer-mapped buffer (`buffer()`), `reduce()` launches ONE kernel that exchanges
     per-CTA flags with the peers, sums all ranks' buffers through NVLink in rank order
     (bit-identical on every rank) and releases the buffer.  ~5 us of host time per call
-    (no NCCL, no dispatcher), chained to the GEMMs with programmatic dependent launch."""
+    (no NCCL, no dispatcher), chained to the GEMMs with programmatic dependent launch.
 
-    def __init__(self, group=None):
+    Invariant of the default (``end_barrier=False``) mode: the two buffers of a slot
+    alternate per ``buffer()`` call, and at least one ``reduce()`` on a buffer's pad lies
+    between a read of that buffer and its next overwrite.  That holds when every
+    ``buffer()`` is followed by its ``reduce()`` and the calls run eagerly.  Under CUDA-graph
+    capture the buffer choice is frozen into the graph: construct with ``end_barrier=True``
+    (or pass it to ``reduce``) when a captured graph holds fewer than two reduces per slot.
+    ``fenced=True`` (or env PETIT_AR_FENCED=1) selects the release/acquire flag protocol."""
+
+    def __init__(self, group=None, end_barrier: bool = False, fenced: bool = False):
         import petit_kernel as pk  # CUDA extension; no fallback
         import torch.distributed._symmetric_memory as symm_mem
 
@@ -113,6 +121,16 @@ class PeerAllReduce:
         self.world = dist.get_world_size(self.group)
         self.slots = {}
         self.by_ptr = {}
+        self.end_barrier = end_barrier
+        self.fenced = fenced
+
+    def status(self) -> int:
+        """0 if every reduce so far met all its peers; 1 + missing rank otherwise
+        (synchronises the current stream)."""
+        worst = 0
+        for entry in self.by_ptr.values():
+            worst = max(worst, int(self.pk.ops.allreduce_status(entry[3])))
+        return worst
 
     def _alloc(self, m: int, n: int, dtype, device):
         pad_elems = self.pk.ops.allreduce_pad_bytes() // 2
@@ -143,15 +161,19 @@ class PeerAllReduce:
         pair[1] ^= 1
         return pair[0][pair[1]]
 
-    def reduce(self, buf: torch.Tensor, out: "torch.Tensor | None" = None) -> torch.Tensor:
+    def reduce(self, buf: torch.Tensor, out: "torch.Tensor | None" = None,
+               end_barrier: "bool | None" = None) -> torch.Tensor:
         entry = self.by_ptr.get(buf.data_ptr())
         if entry is None:
             raise ValueError("buf was not allocated by PeerAllReduce.buffer()")
         view, bufs, pads, epoch = entry[:4]
         if out is None:
             out = torch.empty_like(view)
+        eb = self.end_barrier if end_barrier is None else end_barrier
+        if torch.cuda.is_current_stream_capturing():
+            eb = True  # the buffer parity is frozen into the graph
         return self.pk.ops.allreduce_oneshot(out, bufs, pads, epoch, self.rank, view.numel(),
-                                             False)
+                                             eb, self.fenced)
 
 
 @dataclass

@@ -1,7 +1,14 @@
 """Run under torchrun (world >= 2, one GPU per rank): petit_tp.PeerAllReduce against
-ncclAllReduce on a row-parallel NVFP4 layer.  Launched by tests/test_gpu_parity.py."""
+ncclAllReduce on a row-parallel NVFP4 layer, then a stress loop with data that changes every
+call (a stale read of a peer buffer or a lost flag shows up as a mismatch against NCCL).
+Launched by tests/test_gpu_parity.py and tools/exp_tp_check.sh.
+
+  torchrun --nproc-per-node N tests/tp_peer_allreduce_check.py [iters] [out.json]
+"""
+import json
 import os
 import sys
+import time
 
 import torch
 import torch.distributed as dist
@@ -15,10 +22,7 @@ import petit_tp  # noqa: E402
 from oracle import petit_oracle as orc  # noqa: E402  (checker only)
 
 
-def main():
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-    dist.init_process_group("nccl")
+def gemm_case(rank, world):
     m, n, k = 16, 1024, 2048
     a, q, s, gs = orc.make_nvfp4_case(m, n, k, 77)
     # K-split (row parallel): every rank owns k / world columns
@@ -46,9 +50,53 @@ def main():
         assert all(torch.equal(gathered[0], x) for x in gathered)
     full = orc.nvfp4_gemm_ref_torch(a, q, s, gs)
     assert orc.max_rel_err(got.float().cpu(), full) <= 1e-2
+    assert par.status() == 0
+
+
+def stress(rank, world, iters, end_barrier, fenced, m=16, n=8192):
+    """Integer-valued bf16 data that changes every call: the exact sum is representable, so
+    the peer kernel must match the closed form bit for bit (any stale 16-byte vector from a
+    previous call, a torn read or a missed flag is a mismatch).  A device-side check every
+    call, one host sync per 256 calls."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    par = petit_tp.PeerAllReduce(end_barrier=end_barrier, fenced=fenced)
+    idx = (torch.arange(m * n, device=dev, dtype=torch.int32) % 7).view(m, n)
+    bad = torch.zeros((), dtype=torch.int32, device=dev)
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=dev)
+    t0 = time.time()
+    for it in range(iters):
+        buf = par.buffer(m, n, torch.bfloat16, dev, 1)
+        # rank r contributes (idx + it + r) % 13 - 6  (|.| <= 6, sums <= 48: exact in bf16)
+        buf.copy_(((idx + (it + rank)) % 13 - 6).to(torch.bfloat16))
+        par.reduce(buf, out=out)
+        want = sum(((idx + (it + r)) % 13 - 6) for r in range(world)).to(torch.bfloat16)
+        bad += (out != want).any().to(torch.int32)
+        if it % 256 == 255:
+            assert bad.item() == 0, f"rank {rank}: mismatch by iteration {it}"
+    torch.cuda.synchronize()
+    assert bad.item() == 0, f"rank {rank}: mismatch"
+    assert par.status() == 0
+    return time.time() - t0
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl")
+    iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    gemm_case(rank, world)
+    res = {"world": world, "iters": iters, "modes": []}
+    for end_barrier in (False, True):
+        for fenced in (False, True):
+            secs = stress(rank, world, iters, end_barrier, fenced)
+            res["modes"].append({"end_barrier": end_barrier, "fenced": fenced, "ok": True,
+                                 "seconds": round(secs, 2)})
     dist.barrier()
     if rank == 0:
-        print("PEER_ALLREDUCE_OK")
+        print("PEER_ALLREDUCE_OK", json.dumps(res))
+        if len(sys.argv) > 2:
+            with open(sys.argv[2], "w") as f:
+                json.dump(res, f)
     dist.destroy_process_group()
 
 

@@ -34,6 +34,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <type_traits>
 
 namespace petit::gemm {
 
@@ -52,7 +53,7 @@ namespace {
 
 // Warp roles, aligned to warpgroups so setmaxnreg can rebalance registers:
 //   WG0:   warp 0 = TMA producer (weights), warp 1 = MMA issuer, warp 2 = TMA producer
-//          (token tiles), warp 3 idle
+//          (token tiles), warp 3 = second MMA issuer for decode tiles (idle otherwise)
 //   WG1:   warps 4-7  = epilogue (one per TMEM lane quarter)
 //   WG2-5: warps 8-23 = dequant (4 per lane quarter -> 4 per SM sub-partition)
 // (Measured: putting the two single-thread roles on the highest warp ids instead
@@ -63,6 +64,7 @@ constexpr int kNumEpilogueWarps = 4;
 constexpr int kProducerWarp = 0;    // weights + scales
 constexpr int kMmaWarp = 1;
 constexpr int kActProducerWarp = 2; // token tiles
+constexpr int kMmaWarp2 = 3;        // decode tiles: second MMA issuer (half of the accumulator chains)
 constexpr int kFirstEpilogueWarp = 4;
 constexpr int kFirstDequantWarp = 8;
 constexpr int kNumWarps = kFirstDequantWarp + kNumDequantWarps;
@@ -132,6 +134,11 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     static constexpr int kActiveSlices = kUsedSlices / kGroups;  // k-slice warps per stage
     static constexpr int kStageWarps = 4 * kActiveSlices;        // dequant warps per stage
     static_assert(kChunks % kActiveSlices == 0, "chunks must split evenly over the k-slices");
+    // Decode tiles: two MMA issuers on two SM sub-partitions, each owning half of the
+    // accumulator chains.  One issuer's ~105 instructions per stage behind four dequant warps
+    // of its sub-partition were the critical path of the TMEM hand-off (measured: 15 fewer
+    // instructions per stage in that warp = -9 % on gate_up, profiles/r02_decode_ab.md).
+    static constexpr int kMmaWarps = kChains >= 2 ? 2 : 1;
     static constexpr int kAccBufCols = kChains * NTOK;
     static constexpr int kAccCols = kNumAcc * kAccBufCols;
     static_assert(KS / 16 >= kChains, "stage must cover every accumulator chain");
@@ -341,14 +348,14 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             mbar_init(&bars->full[i], 1);
             mbar_init(&bars->full_act[i], 1);
             mbar_init(&bars->empty[i], C::kStageWarps);
-            mbar_init(&bars->empty_act[i], CL ? 2 : 1);
+            mbar_init(&bars->empty_act[i], CL ? 2 : C::kMmaWarps);
         }
         for (int i = 0; i < C::kAStages; ++i) {
             mbar_init(&bars->a_full[i], C::kStageWarps);
-            mbar_init(&bars->a_empty[i], 1);
+            mbar_init(&bars->a_empty[i], C::kMmaWarps);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars->acc_full[i], 1);
+            mbar_init(&bars->acc_full[i], C::kMmaWarps);
             mbar_init(&bars->acc_empty[i], kNumEpilogueWarps * C::kEpiTeams);
         }
         mbar_init(&bars->part_full, 1);
@@ -460,12 +467,20 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             }
             u += g.kt1 - g.kt0;
         }
-    } else if (warp == kMmaWarp) {
-        // ===================== MMA issuer =====================
+    } else if (warp == kMmaWarp || (C::kMmaWarps == 2 && warp == kMmaWarp2)) {
+        // ===================== MMA issuer(s) =====================
+        // Decode tiles: warp 1 issues the k-steps of the lower half of the accumulator chains,
+        // warp 3 those of the upper half (a chain is only ever touched by one thread, so the
+        // MMAs of a chain stay ordered); both commit to the stage barriers (count 2).
         constexpr uint32_t idesc = make_idesc_f16(
             C::kIsBf16 ? kFmtBF16 : kFmtF16, C::kIsBf16 ? kFmtBF16 : kFmtF16, 128, NTOK);
+        constexpr int kHalfChains = C::kChains / C::kMmaWarps;
         const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(stage_base));
-        uint32_t it = 0, seg = 0;
+        auto mma_loop = [&](auto upper_tag) {
+        constexpr bool kUpper = decltype(upper_tag)::value; // this warp owns the upper chains
+        uint64_t bdesc_s = bdesc0;
+        uint32_t a_tmem = tmem_a0;
+        uint32_t s = 0, ph = 0, ta = 0, ta_ph = 0, seg = 0;
         for (uint32_t u = u_begin; u < u_end; ++seg) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t acc = seg % C::kNumAcc;
@@ -474,26 +489,22 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             tc_fence_after();
             const uint32_t d_tmem = tmem + acc * C::kAccBufCols;
             const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
-            for (uint32_t i = 0; i < n_stage; ++i, ++it) {
-                const uint32_t s = it % C::kStages;
-                const uint32_t ph = (it / C::kStages) & 1;
-                const uint32_t ta = it % C::kAStages;
-                const uint32_t ta_ph = (it / C::kAStages) & 1;
+            for (uint32_t i = 0; i < n_stage; ++i) {
                 mbar_wait(&bars->full_act[s], ph);  // token tile landed
-                if (it == 0 && lane == 0) trace_stamp(args, 3);
+#ifdef PETIT_DEBUG_HOOKS
+                if (seg == 0 && i == 0 && lane == 0) trace_stamp(args, 3);
+#endif
                 mbar_wait(&bars->a_full[ta], ta_ph); // weights are in TMEM
                 tc_fence_after();
-                if (lane == 0) trace_stage(args, it, 5);
                 if (elect_one()) {
-                    const uint64_t bdesc_s = bdesc0 + (uint64_t)((s * C::kStageBytes) >> 4);
-                    const uint32_t a_tmem = tmem_a0 + ta * C::kACols;
 #pragma unroll
                     for (int j = 0; j < KS / 16; ++j) {
-                        if (PETIT_DBG(args.debug_flags, 1u) && j != 0) continue; // experiment: 1 MMA/stage
+                        const int chain = j % C::kChains;
+                        if (C::kMmaWarps == 2 && (chain >= kHalfChains) != kUpper) continue;
                         const uint64_t bdesc =
                             bdesc_s + (uint64_t)(((j / 4) * (NTOK * 128) + (j % 4) * 32) >> 4);
-                        mma_f16_ts(d_tmem + (j % C::kChains) * NTOK, a_tmem + j * 8, bdesc,
-                                   idesc, (i != 0 || j >= C::kChains) ? 1u : 0u);
+                        mma_f16_ts(d_tmem + chain * NTOK, a_tmem + j * 8, bdesc, idesc,
+                                   (i != 0 || j >= C::kChains) ? 1u : 0u);
                     }
                     tc_commit(&bars->a_empty[ta]);
                     if (CL)
@@ -501,13 +512,21 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     else
                         tc_commit(&bars->empty_act[s]);
                     if (i + 1 == n_stage) tc_commit(&bars->acc_full[acc]);
-                    trace_stage(args, it, 6);
                 }
                 __syncwarp();
+                bdesc_s += (uint64_t)(C::kStageBytes >> 4);
+                a_tmem += C::kACols;
+                if (++s == (uint32_t)C::kStages) { s = 0; ph ^= 1; bdesc_s = bdesc0; }
+                if (++ta == (uint32_t)C::kAStages) { ta = 0; ta_ph ^= 1; a_tmem = tmem_a0; }
             }
             u += g.kt1 - g.kt0;
         }
-        if (lane == 0) trace_stamp(args, 5);
+        };
+        if (C::kMmaWarps == 2 && warp == kMmaWarp2)
+            mma_loop(std::true_type{});
+        else
+            mma_loop(std::false_type{});
+        if (lane == 0 && warp == kMmaWarp) trace_stamp(args, 5);
     } else if (warp >= kFirstDequantWarp &&
                (warp - kFirstDequantWarp) / 4 < (uint32_t)C::kUsedSlices) {
         // ===================== dequant warps =====================

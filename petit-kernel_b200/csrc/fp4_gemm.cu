@@ -31,6 +31,7 @@
 #include "layout.cuh"
 #include "sm100_ptx.cuh"
 
+#include <cstddef>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -46,7 +47,13 @@ using namespace petit::dq;
 #define PETIT_DECODE_GROUPS 2
 #endif
 #ifndef PETIT_DECODE_GROUPS_NVBF16
-#define PETIT_DECODE_GROUPS_NVBF16 1
+#define PETIT_DECODE_GROUPS_NVBF16 2
+#endif
+// Knock-out experiments (tools/build_variant.sh <name> . -DPETIT_KO=<bits>; results are wrong on
+// purpose, timing only): 1 = two MMAs per issuer and stage, 2 = no dequant arithmetic, 16 = no
+// TMEM stores (arithmetic kept alive), 32 = no tcgen05.wait::st.  0 in production.
+#ifndef PETIT_KO
+#define PETIT_KO 0
 #endif
 
 namespace {
@@ -121,11 +128,11 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     // Prefill tiles (NTOK >= 128) are tensor-bound: only half of the dequant warps
     // work there, the rest would just compete with the MMA issuer for issue slots.
     static constexpr int kUsedSlices = NTOK >= 128 ? kKSlices / 2 : kKSlices;
-    // Decode tiles (NTOK <= 64), fp16 and MXFP4 only: two groups of 8 warps take
-    // alternate 256-k stages, 4 chunks per thread, which halves the per-stage
-    // bookkeeping per weight (measured gate_up M=16: fp16 76 -> 71 us, MXFP4 77 -> 65 us;
-    // NVFP4-bf16 is no faster with two groups -- 57.9 vs 58.0 us, -DPETIT_DECODE_GROUPS_NVBF16=2,
-    // profiles/r01_variants_ab.log -- so it keeps 1 group).
+    // Decode tiles (NTOK <= 64): two groups of 8 warps take alternate 256-k stages, 4 chunks
+    // per thread, which halves the per-stage bookkeeping per weight (measured gate_up M=16:
+    // fp16 76 -> 71 us, MXFP4 77 -> 65 us; NVFP4-bf16 was neutral while the single MMA issuer
+    // was the critical path -- profiles/r01_variants_ab.log -- and gains 3 % with two issuers:
+    // 53.2 -> 51.5 us, profiles/r02_decode_ab.md).
     static constexpr int kGroups =
         kUsedSlices > kChunks ? kUsedSlices / kChunks
                               : (NTOK <= 64 ? (MODE != kModeNvBf16 ? PETIT_DECODE_GROUPS
@@ -290,6 +297,17 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 template <bool kBf16> __device__ __forceinline__ uint16_t to_bits16(float r) {
     if (kBf16) return __bfloat16_as_ushort(__float2bfloat16_rn(r));
     return __half_as_ushort(__float2half_rn(r));
+}
+
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra D;\n\tbra W;\n\tD:\n\t}" ::"r"(bar_addr),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -499,6 +517,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 if (elect_one()) {
 #pragma unroll
                     for (int j = 0; j < KS / 16; ++j) {
+                        if ((PETIT_KO & 1) && j >= 4) continue; // experiment: fewer MMAs
                         const int chain = j % C::kChains;
                         if (C::kMmaWarps == 2 && (chain >= kHalfChains) != kUpper) continue;
                         const uint64_t bdesc =
@@ -553,6 +572,90 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             while (clock64() - t0 < wait) {
             }
         }
+        // Fast path (every n-tile has 128 rows -- all Llama shapes): the weight stream is one
+        // continuous sequence of stages, nothing in it depends on which output tile a stage
+        // belongs to, so the loop runs flat over this CTA's stages (no per-segment state), a
+        // group steps straight to its own stages, and every shared-memory offset is an
+        // immediate.  Ring state lives in running addresses (no multiplies / modulo).
+        if (args.n % kTileN == 0) {
+            constexpr uint32_t kG = C::kGroups;
+            const uint32_t total = (u_end - u_begin) * C::kStagesPerUnit;
+            const uint32_t bars_addr = smem_u32(bars);
+            const uint32_t full_b = bars_addr + (uint32_t)offsetof(Barriers, full);
+            const uint32_t aempty_b = bars_addr + (uint32_t)offsetof(Barriers, a_empty);
+            constexpr uint32_t kFullToEmpty = (uint32_t)(offsetof(Barriers, empty) - offsetof(Barriers, full));
+            constexpr int32_t kEmptyToFullA = (int32_t)offsetof(Barriers, a_full) - (int32_t)offsetof(Barriers, a_empty);
+            const uint32_t lane_off = (c0 * kTileN + row) * 16;
+            const uint32_t sc_lane_off = C::kWBytes + ((c0 / 2) * kTileN + row) * C::kScPerSub +
+                                         (c0 & 1) * kScBytesPerChunk;
+            const uint32_t st0 = w_base + lane_off, sc0 = w_base + sc_lane_off;
+            // position of this group's first stage
+            uint32_t sidx = group % C::kStages, ph2 = 0, aidx = group % C::kAStages, aph = 1;
+            uint32_t st_w = st0 + sidx * C::kStageBytes, st_sc = sc0 + sidx * C::kStageBytes;
+            uint32_t fb = full_b + sidx * 8, ab = aempty_b + aidx * 8;
+            uint32_t tm = tmem_dst + aidx * C::kACols;
+            const bool lane0 = lane == 0;
+            for (uint32_t it = group; it < total; it += kG) {
+                mbar_wait_addr(fb, ph2);
+                uint4 q[kMyChunks];
+#pragma unroll
+                for (int ci = 0; ci < kMyChunks; ++ci) q[ci] = lds_v4(st_w + ci * (kTileN * 16));
+                constexpr int kScLoads = kMyChunks >= 2 ? kMyChunks / 2 : 1;
+                uint32_t scw[kScLoads];
+#pragma unroll
+                for (int p = 0; p < kScLoads; ++p) {
+                    const uint32_t a = st_sc + p * (kTileN * C::kScPerSub);
+                    if (kMyChunks >= 2)
+                        scw[p] = C::kIsMx ? lds_u16(a) : lds_u32(a);
+                    else
+                        scw[p] = C::kIsMx ? lds_u8(a) : lds_u16(a);
+                }
+                // the previous occupant of this TMEM A stage must have been consumed
+                mbar_wait_addr(ab, aph);
+                tc_fence_after();
+#pragma unroll
+                for (int ci = 0; ci < kMyChunks; ++ci) {
+                    const uint32_t bits = scw[ci / 2] >> ((ci & 1) * 8 * kScBytesPerChunk);
+                    bool two_step = false;
+                    if (C::kIsMx) two_step = __any_sync(0xffffffffu, mx_needs_two_step(bits));
+                    const uint32_t mult = chunk_multiplier<MODE>(bits, two_step);
+                    uint32_t out[16];
+#if PETIT_KO & 2
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) out[j] = q[ci].x + j;
+#else
+                    dequant_chunk<MODE>(q[ci], mult, two_step, out);
+#endif
+#if PETIT_KO & 16
+                    asm volatile("" ::"r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3]), "r"(out[4]),
+                                 "r"(out[5]), "r"(out[6]), "r"(out[7]), "r"(out[8]), "r"(out[9]),
+                                 "r"(out[10]), "r"(out[11]), "r"(out[12]), "r"(out[13]),
+                                 "r"(out[14]), "r"(out[15]));
+#else
+                    tmem_st_x16(tm + ci * 16, out);
+#endif
+                }
+                if (!(PETIT_KO & 32)) tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane0) {
+                    mbar_arrive_addr((uint32_t)((int32_t)ab + kEmptyToFullA)); // a_full[aidx]
+                    mbar_arrive_addr(fb + kFullToEmpty);                        // empty[sidx]
+                }
+                // step to this group's next stage
+                sidx += kG; st_w += kG * C::kStageBytes; st_sc += kG * C::kStageBytes; fb += kG * 8;
+                if (sidx >= (uint32_t)C::kStages) {
+                    sidx -= C::kStages; ph2 ^= 1;
+                    st_w -= C::kStages * C::kStageBytes; st_sc -= C::kStages * C::kStageBytes;
+                    fb -= C::kStages * 8;
+                }
+                aidx += kG; ab += kG * 8; tm += kG * C::kACols;
+                if (aidx >= (uint32_t)C::kAStages) {
+                    aidx -= C::kAStages; aph ^= 1;
+                    ab -= C::kAStages * 8; tm -= C::kAStages * C::kACols;
+                }
+            }
+        } else
         for (uint32_t u = u_begin; u < u_end;) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t rows = tile_rows(args.n, g.n_tile);

@@ -95,7 +95,14 @@ typedef struct PetitSolutionHints {
 
 /* C[m,n] (a_type) = A[m,k] (a_type, row-major) x dequant(B)[n,k]^T x *global_scale.
  * b / scales are the outputs of petit_repack_fp4_weights / petit_repack_nvfp4_scales.
- * Requires k % 256 == 0 and n % 16 == 0 (lib/pybind/fp4.cc:40-43,82-86). */
+ * Requires k % 256 == 0 and n % 16 == 0 (lib/pybind/fp4.cc:40-43,82-86).
+ * Ordering: the GEMM is launched with programmatic dependent launch and starts streaming
+ * b / scales while the previous kernel on the stream drains; a, global_scale and c are
+ * touched only after that kernel has completed.  b / scales must therefore be complete before
+ * the kernel that precedes the GEMM on the stream was launched -- true for weights, which
+ * are constants; a GEMM that directly follows a petit_repack_* call on the same stream is
+ * ordered behind it by the library; anything else that rewrites weights immediately before a
+ * GEMM sets PETIT_PDL=0. */
 int petit_gemm_nvfp4_a16(void *c, const void *a, const void *b, const void *scales,
                          const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
                          const PetitSolutionHints *hints, uint64_t solution_id,
@@ -205,6 +212,22 @@ int petit_allreduce_status(const void *epoch, petit_stream_t stream);
 int petit_allreduce_oneshot(void *out, const void *const *peer_bufs, void *const *peer_pads,
                             void *epoch, int rank, int world, size_t numel, int dtype,
                             int end_barrier, petit_stream_t stream);
+
+/* Stream-K workspace (library-owned, one per (device, stream), ~25 MB, created on the first
+ * GEMM of a stream, at most 16 alive).  GEMMs that cut output tiles between CTAs let one CTA
+ * wait for the partial sums of CTAs with higher block ids, which publish as soon as they are
+ * resident; that needs the grid (<= one CTA per SM) to become co-resident.  GEMMs issued on
+ * ONE stream, or on several streams of EQUAL priority, always get there (CTAs are dispatched
+ * grid after grid).  Two such GEMMs interleaved by streams of DIFFERENT priority can starve
+ * each other: then the waiting CTA gives up after PETIT_WATCHDOG_MS (default 2000) and
+ * petit_workspace_status reports it.
+ *   petit_workspace_status: synchronises `stream`; *status = 0 if no reducer of a GEMM on this
+ *     stream ever timed out, else 1 + the output tile that did (that GEMM's output is wrong;
+ *     release the workspace before the next call).
+ *   petit_release_workspace: synchronises `stream` and frees its workspace (a later GEMM on
+ *     the stream creates a fresh one).  Not allowed while the stream is being captured. */
+int petit_workspace_status(petit_stream_t stream, int *status);
+int petit_release_workspace(petit_stream_t stream);
 
 /* Version of the packed layouts produced by the repack functions. */
 int petit_packed_layout_version(void);

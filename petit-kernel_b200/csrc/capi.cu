@@ -18,8 +18,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <mutex>
+#include <set>
 #include <tuple>
 #include <utility>
 #include <vector>
@@ -173,7 +175,7 @@ Decoded default_solution(bool is_mx, int a_type, unsigned m, unsigned n, unsigne
 // ---- per-(device, stream) stream-K workspace --------------------------------
 struct Workspace {
     float *partials = nullptr;
-    unsigned *counters = nullptr;
+    unsigned *counters = nullptr; // kMaxTiles tile counters + 1 status word
 };
 struct DeviceInfo {
     int num_sms = 0;
@@ -181,6 +183,27 @@ struct DeviceInfo {
 unsigned long long *g_trace = nullptr; // set by petit_debug_set_trace
 std::mutex g_mu;
 std::map<std::pair<int, cudaStream_t>, Workspace> g_ws;
+std::deque<std::pair<int, cudaStream_t>> g_ws_order; // creation order, for the cap below
+constexpr size_t kMaxWorkspaces = 16;                // x ~25 MB each
+// Streams whose most recent petit call wrote packed weights / scales (repack_*): the weight
+// producer warp of the GEMM does not execute griddepcontrol.wait (weights are constants), so
+// a GEMM that directly follows such a call on the same stream is launched without
+// programmatic dependent launch and therefore fully ordered behind it.
+std::set<std::pair<int, cudaStream_t>> g_wrote_weights;
+
+void note_weight_writer(cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_wrote_weights.insert(std::make_pair(dev, stream));
+}
+// true (and forgotten) if the previous petit call on this stream wrote weights
+bool take_weight_writer(cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    std::lock_guard<std::mutex> lock(g_mu);
+    return g_wrote_weights.erase(std::make_pair(dev, stream)) != 0;
+}
 std::map<int, DeviceInfo> g_dev;
 
 int get_context(cudaStream_t stream, Workspace *ws, int *num_sms) {
@@ -203,23 +226,45 @@ int get_context(cudaStream_t stream, Workspace *ws, int *num_sms) {
     auto key = std::make_pair(dev, stream);
     auto it = g_ws.find(key);
     if (it == g_ws.end()) {
-        // cudaMalloc is not capturable: step out of a possible stream capture.
+        // cudaMalloc is not capturable: step out of a possible stream capture.  The counters
+        // are zeroed EAGERLY on an internal stream and waited for here, so the zeroing is
+        // never recorded into a graph being captured on `stream` (it would then only run when
+        // that one graph is replayed, and again on every replay) and is complete before any
+        // later work -- eager or captured, on any stream -- can touch the workspace.
         cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
         cudaThreadExchangeStreamCaptureMode(&mode);
         Workspace w;
+        cudaStream_t init = nullptr;
         cudaError_t e1 = cudaMalloc(&w.partials, gemm::workspace_partials_bytes());
         cudaError_t e2 = cudaMalloc(&w.counters, gemm::workspace_counters_bytes());
-        // ordered on the caller's stream ahead of the first GEMM (a plain cudaMemset runs
-        // on the legacy stream, which non-blocking streams do not wait for)
-        cudaError_t e3 = e2 == cudaSuccess ? cudaMemsetAsync(w.counters, 0,
-                                                             gemm::workspace_counters_bytes(), stream)
-                                           : e2;
+        cudaError_t e3 = cudaStreamCreateWithFlags(&init, cudaStreamNonBlocking);
+        if (e2 == cudaSuccess && e3 == cudaSuccess)
+            e3 = cudaMemsetAsync(w.counters, 0, gemm::workspace_counters_bytes(), init);
+        if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(init);
+        if (init) cudaStreamDestroy(init);
         cudaThreadExchangeStreamCaptureMode(&mode);
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
             cudaFree(w.partials);
             cudaFree(w.counters);
             return PETIT_ERROR_CUDA;
         }
+        // keep the footprint bounded: a process that cycles through many streams (torch's
+        // stream pool) drops the workspaces of the least recently created streams
+        if (g_ws.size() >= kMaxWorkspaces) {
+            auto victim = g_ws_order.front();
+            g_ws_order.pop_front();
+            auto vit = g_ws.find(victim);
+            if (vit != g_ws.end()) {
+                // the victim's stream may still run a GEMM: let it drain before freeing
+                cudaStreamCaptureMode m2 = cudaStreamCaptureModeRelaxed;
+                cudaThreadExchangeStreamCaptureMode(&m2);
+                cudaFree(vit->second.partials); // cudaFree synchronises the device
+                cudaFree(vit->second.counters);
+                cudaThreadExchangeStreamCaptureMode(&m2);
+                g_ws.erase(vit);
+            }
+        }
+        g_ws_order.push_back(key);
         it = g_ws.emplace(key, w).first;
     }
     *ws = it->second;
@@ -276,6 +321,15 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
     args.c = c;
     args.ws_partials = ws.partials;
     args.ws_counters = ws.counters;
+    args.ws_status = ws.counters + gemm::kMaxTiles;
+    {
+        static const unsigned long long wd = [] {
+            const char *e = std::getenv("PETIT_WATCHDOG_MS");
+            const long long ms = e ? std::atoll(e) : 2000;
+            return (unsigned long long)(ms > 0 ? ms : 2000) * 1000000ull;
+        }();
+        args.watchdog_ns = wd;
+    }
     args.m = m;
     args.n = n;
     args.k = k;
@@ -286,6 +340,7 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
             return e ? std::atoi(e) : 1;
         }();
         args.use_pdl = (uint32_t)pdl;
+        if (take_weight_writer(stream)) args.use_pdl = 0;
         static const int cl = [] {
             const char *e = std::getenv("PETIT_CLUSTER");
             return e ? std::atoi(e) : 1;
@@ -408,6 +463,7 @@ void petit_tune_table_clear(void) {
 
 int petit_repack_fp4_weights(uint32_t *out, const uint32_t *in, unsigned in_chan,
                              unsigned out_chan, petit_stream_t stream) {
+    note_weight_writer(reinterpret_cast<cudaStream_t>(stream));
     return repack::weights(out, in, in_chan, out_chan, false,
                            reinterpret_cast<cudaStream_t>(stream));
 }
@@ -420,12 +476,14 @@ int petit_unpack_fp4_weights(uint32_t *out, const uint32_t *in_packed, unsigned 
 
 int petit_repack_nvfp4_scales(void *out, const void *in, unsigned in_chan, unsigned out_chan,
                               petit_stream_t stream) {
+    note_weight_writer(reinterpret_cast<cudaStream_t>(stream));
     return repack::scales(out, in, in_chan, out_chan, false, false,
                           reinterpret_cast<cudaStream_t>(stream));
 }
 
 int petit_repack_mxfp4_scales(void *out, const void *in, unsigned in_chan, unsigned out_chan,
                               petit_stream_t stream) {
+    note_weight_writer(reinterpret_cast<cudaStream_t>(stream));
     return repack::scales(out, in, in_chan, out_chan, true, false,
                           reinterpret_cast<cudaStream_t>(stream));
 }
@@ -481,6 +539,53 @@ int petit_hal_copy_to_host(void *dst, const void *src, size_t bytes) {
 int petit_hal_synchronize(void) { return (int)cudaDeviceSynchronize(); }
 
 int petit_packed_layout_version(void) { return layout::kLayoutVersion; }
+
+int petit_workspace_status(petit_stream_t stream, int *status) {
+    if (!status) return -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PETIT_ERROR_CUDA;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    unsigned *word = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto it = g_ws.find(std::make_pair(dev, s));
+        if (it == g_ws.end()) {
+            *status = 0; // no GEMM has run on this stream yet
+            return PETIT_OK;
+        }
+        word = it->second.counters + gemm::kMaxTiles;
+    }
+    unsigned v = 0;
+    if (cudaMemcpyAsync(&v, word, sizeof v, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+        return PETIT_ERROR_CUDA;
+    *status = (int)v;
+    return PETIT_OK;
+}
+
+int petit_release_workspace(petit_stream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PETIT_ERROR_CUDA;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    Workspace w;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto key = std::make_pair(dev, s);
+        auto it = g_ws.find(key);
+        if (it == g_ws.end()) return PETIT_OK;
+        w = it->second;
+        g_ws.erase(it);
+        for (auto o = g_ws_order.begin(); o != g_ws_order.end(); ++o)
+            if (*o == key) {
+                g_ws_order.erase(o);
+                break;
+            }
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess) return PETIT_ERROR_CUDA;
+    cudaFree(w.partials);
+    cudaFree(w.counters);
+    return PETIT_OK;
+}
 
 // Debug hook (not in petit.h): device buffer of [grid][16] u64 globaltimer stamps.
 void petit_debug_set_trace(unsigned long long *dev_buffer) { g_trace = dev_buffer; }

@@ -22,15 +22,17 @@
 //  * stream-K: the (n-tile x token-tile x k-tile) unit space is cut into one
 //    contiguous range per SM, so all 148 SMs stream the same number of bytes
 //    whatever the shape.  Tiles cut by a range boundary are reduced through an
-//    fp32 workspace by the last CTA to arrive, in a fixed order (bit-reproducible).
-//  * warp roles: 2 TMA producers (weights / token tiles), 1 MMA issuer, 16 dequant
-//    warps, 4 epilogue warps; accumulators are double-buffered in TMEM so the
-//    epilogue overlaps the next tile.
+//    fp32 workspace by the CTA that owns the tile's first k-part (a static choice: it
+//    reaches the tile last, at the end of its range), in CTA order (bit-reproducible).
+//  * warp roles: 2 TMA producers (weights / token tiles), 1 MMA issuer (2 for decode
+//    tiles, each owning half of the accumulator chains), 16 dequant warps, 4 epilogue
+//    warps; accumulators are double-buffered in TMEM so the epilogue overlaps the next tile.
 #include "fp4_gemm.h"
 #include "dequant.cuh"
 #include "layout.cuh"
 #include "sm100_ptx.cuh"
 
+#include <atomic>
 #include <cstddef>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -785,14 +787,32 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             if (lead && last_seg) trace_stamp(args, 11);
             if (is_reducer) {
                 if (lead) {
+                    // The contributors are CTAs with higher block ids.  They never wait for
+                    // anyone, so they publish as soon as they are resident -- which needs the
+                    // whole grid (<= one CTA per SM) to become co-resident.  Another grid that
+                    // holds SMs and itself waits (two stream-K GEMMs interleaved by a
+                    // high-priority stream) could keep them out for ever: a watchdog turns that
+                    // hang into a reported error (petit_workspace_status) and the CTA goes on
+                    // with what it has.
                     const uint32_t need = b_last - b_first;
-                    uint32_t seen;
-                    do {
+                    uint32_t seen, spins = 0;
+                    unsigned long long t_start = 0;
+                    for (;;) {
                         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
                                      : "=r"(seen)
                                      : "l"(args.ws_counters + out_tile)
                                      : "memory");
-                    } while (seen < need);
+                        if (seen >= need) break;
+                        if ((++spins & 0x3ff) == 0) {
+                            unsigned long long now;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                            if (t_start == 0) t_start = now;
+                            if (now - t_start > args.watchdog_ns) {
+                                atomicExch(args.ws_status, 1u + out_tile);
+                                break;
+                            }
+                        }
+                    }
                     if (last_seg) trace_stamp(args, 12);
                 }
                 named_bar_sync(kEpilogueBarId, kAllEpiThreads);
@@ -1013,15 +1033,15 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return kLaunchCudaError;
 
-    static bool attr_set[64] = {}; // per instantiation, per device
+    static std::atomic<bool> attr_set[64]; // per instantiation, per device (zero-initialised)
     auto kern = fp4_gemm_kernel<MODE, NTOK, KS, CL>;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return kLaunchCudaError;
-    if (!attr_set[dev & 63]) {
+    if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  C::kSmemBytes) != cudaSuccess)
             return kLaunchCudaError;
-        attr_set[dev & 63] = true;
+        attr_set[dev & 63].store(true, std::memory_order_release);
     }
     const uint64_t n_tiles = (args.n + kTileN - 1) / kTileN;
     const uint64_t m_tiles = (args.m + NTOK - 1) / NTOK;
@@ -1076,7 +1096,7 @@ template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
 size_t workspace_partials_bytes() {
     return (size_t)kMaxGrid * kTileN * 256 * sizeof(float);
 }
-size_t workspace_counters_bytes() { return (size_t)kMaxTiles * sizeof(unsigned); }
+size_t workspace_counters_bytes() { return ((size_t)kMaxTiles + 1) * sizeof(unsigned); }
 
 int launch(int mode, int ntok, const GemmArgs &args, int num_sms, cudaStream_t stream) {
     switch (mode) {

@@ -21,6 +21,8 @@ struct GemmArgs {
     void *c;                // [m, n] 16-bit row-major
     float *ws_partials;     // stream-K partial tiles
     unsigned *ws_counters;  // per-tile arrival counters (zero between launches)
+    unsigned *ws_status;    // sticky: != 0 once a split-tile reducer gave up waiting (watchdog)
+    unsigned long long watchdog_ns; // how long a reducer polls for its contributors
     uint32_t m, n, k;
     uint32_t debug_flags;   // experiments only (PETIT_DEBUG_FLAGS); 0 in production
     uint32_t use_cluster;   // allow the 2-CTA multicast variant for 128/256-token tiles
@@ -30,7 +32,7 @@ struct GemmArgs {
 };
 
 size_t workspace_partials_bytes();
-size_t workspace_counters_bytes();
+size_t workspace_counters_bytes(); // kMaxTiles counters + the status word (last)
 
 // ntok: tokens per MMA (16, 32, 64, 128, 256).
 int launch(int mode, int ntok, const GemmArgs &args, int num_sms, cudaStream_t stream);

@@ -471,4 +471,15 @@ PYBIND11_MODULE(ops, m) {
     m.def("tune_table_clear", []() { petit_tune_table_clear(); });
     m.def("solution_name", [](uint64_t id) { return std::string(petit_solution_name(id)); });
     m.def("packed_layout_version", []() { return petit_packed_layout_version(); });
+    // stream-K workspace of the current stream: watchdog status and explicit release
+    m.def("workspace_status", []() {
+        int st = 0;
+        int rc = petit_workspace_status(at::cuda::getCurrentCUDAStream().stream(), &st);
+        TORCH_CHECK(rc == 0, "petit_workspace_status failed with code ", rc);
+        return (int64_t)st;
+    });
+    m.def("release_workspace", []() {
+        int rc = petit_release_workspace(at::cuda::getCurrentCUDAStream().stream());
+        TORCH_CHECK(rc == 0, "petit_release_workspace failed with code ", rc);
+    });
 }

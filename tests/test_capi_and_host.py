@@ -340,16 +340,3 @@ def test_percta_trace_tool_summarises_the_committed_traces():
     for gemm in ("qkv", "o", "gate_up", "down"):
         assert f"== {gemm} launch 1, 148 CTAs" in out
     assert out.count("griddep_wait_done") == 4 and out.count("late cta") == 24
-
-
-def test_variant_patches_still_apply_to_the_kernel_source():
-    """tools/variant_patches/*.patch are prepared experiments (built by tools/build_variant.sh
-    --patch on a scratch copy); they must not rot against csrc/."""
-    import glob
-
-    patches = sorted(glob.glob(os.path.join(ROOT, "tools", "variant_patches", "*.patch")))
-    assert patches
-    for p in patches:
-        r = subprocess.run(["patch", "--dry-run", "-s", "-p0", "-i", p], cwd=ROOT,
-                           capture_output=True, text=True)
-        assert r.returncode == 0, f"{os.path.basename(p)}: {r.stdout}{r.stderr}"

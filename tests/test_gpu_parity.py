@@ -273,6 +273,86 @@ def test_cuda_graph_capture_reads_global_scale_on_device(pk):
     torch.testing.assert_close(c.float(), 2 * c1.float(), rtol=1e-2, atol=1e-2)
 
 
+def test_two_graphs_captured_on_a_fresh_stream_replay_in_any_order(pk):
+    """The stream-K workspace of a stream is created lazily; when the first GEMM on a stream
+    runs inside graph capture its counters must still be zeroed eagerly, not as a node of that
+    one graph: capture two graphs on a fresh stream, replay the SECOND first."""
+    m, n, k = 16, 2048, 4096   # stream-K splits every tile here
+    a, q, s, gs = orc.make_nvfp4_case(m, n, k, 11)
+    b, sp = pack_nvfp4(pk, q, s, n, k)
+    ac, gsc = a.cuda(), gs.cuda()
+    want = pk.mul_nvfp4_a16(ac, b, sp, gsc, m, n, k, -1)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    outs, graphs = [], []
+    for _ in range(2):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            outs.append(pk.mul_nvfp4_a16(ac, b, sp, gsc, m, n, k, -1))
+        graphs.append(g)
+    for o in outs:
+        o.zero_()
+    torch.cuda.synchronize()
+    graphs[1].replay()
+    torch.cuda.synchronize()
+    assert torch.equal(outs[1], want)
+    graphs[0].replay()
+    graphs[1].replay()
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], want) and torch.equal(outs[1], want)
+
+
+def test_concurrent_streams_split_tile_gemms(pk):
+    """Stream-K GEMMs (every tile split between CTAs) issued concurrently from three streams,
+    one of them high priority, 300 rounds: bit-identical results, no watchdog report.
+    (petit.h documents why equal-priority streams always make progress and what the
+    watchdog does otherwise.)"""
+    m, n, k = 16, 2048, 4096
+    cases = []
+    for seed in (21, 22, 23):
+        a, q, s, gs = orc.make_nvfp4_case(m, n, k, seed)
+        b, sp = pack_nvfp4(pk, q, s, n, k)
+        cases.append((a.cuda(), b, sp, gs.cuda()))
+    want = [pk.mul_nvfp4_a16(a, b, sp, gs, m, n, k, -1) for a, b, sp, gs in cases]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream(priority=-1)]
+    outs = [torch.empty_like(w) for w in want]
+    bad = torch.zeros(3, dtype=torch.int32, device="cuda")
+    for it in range(300):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                a, b, sp, gs = cases[i]
+                pk.ops.mul_nvfp4_a16_out(outs[i], a, b, sp, gs, m, n, k, -1)
+                bad[i] += (outs[i] != want[i]).any().to(torch.int32)
+    torch.cuda.synchronize()
+    assert bad.tolist() == [0, 0, 0]
+    for st in streams:
+        with torch.cuda.stream(st):
+            assert pk.ops.workspace_status() == 0
+            pk.ops.release_workspace()
+    assert pk.ops.workspace_status() == 0
+
+
+def test_gemm_directly_after_repack_on_the_same_stream(pk):
+    """The weight producer warp does not wait for the grid dependency (weights are constants);
+    a GEMM that directly follows repack_* on the stream must still see the repacked weights
+    (the library launches it without programmatic dependent launch)."""
+    m, n, k = 16, 4096, 4096
+    a, q, s, gs = orc.make_nvfp4_case(m, n, k, 31)
+    ac, gsc = a.cuda(), gs.cuda()
+    qw = q.cuda().contiguous().view(torch.int32)
+    sc = s.cuda()
+    b0, sp0 = pack_nvfp4(pk, q, s, n, k)
+    want = pk.mul_nvfp4_a16(ac, b0, sp0, gsc, m, n, k, -1)
+    torch.cuda.synchronize()
+    for _ in range(20):
+        sp = pk.process_nvfp4_scales(sc, n, k)
+        b = pk.repack_nvfp4(qw, n, k)
+        c = pk.mul_nvfp4_a16(ac, b, sp, gsc, m, n, k, -1)
+        assert torch.equal(c, want)
+        del b, sp
+
+
 # ------------------------------------------------------------------ full-size properties
 @pytest.mark.parametrize("name,n,k", [("qkv", 10240, 8192), ("o", 8192, 8192), ("down", 8192, 28672)])
 @pytest.mark.parametrize("fmt", ["nvfp4", "mxfp4"])

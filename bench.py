@@ -214,15 +214,31 @@ def main():
     acts = {k: torch.randn((m, k), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
             for k in {k for _, _, k, _ in shard}}
 
-    # row-parallel outputs (o, down): PETIT_TP_ALLREDUCE = peer (default) | nccl | symm
+    # row-parallel outputs (o, down): PETIT_TP_ALLREDUCE = fused (default) | peer | nccl | symm
+    #   fused: ONE kernel per rank computes the K-split GEMM and all-reduces its output -- the
+    #         CTA that finishes a tile pushes its partial to the peers over NVLink and sums
+    #         theirs (csrc/fp4_gemm.cu "fused all-reduce", petit_tp.FusedAllReduce);
     #   peer: the GEMM writes into a peer-mapped buffer and this package's one-shot
     #         all-reduce kernel (csrc/allreduce.cu) sums all ranks' buffers over NVLink --
     #         one PDL-chained launch, ~5 us of host time;
     #   nccl: dist.all_reduce; symm: torch.ops.symm_mem.one_shot_all_reduce.
     symm = None
     peer = None
+    fused = None
     allreduce_kind = "none" if world == 1 else "nccl"
-    want_ar = os.environ.get("PETIT_TP_ALLREDUCE", "peer")
+    want_ar = os.environ.get("PETIT_TP_ALLREDUCE", "fused")
+    if world > 1 and want_ar == "fused" and m <= 64:
+        try:
+            fused = petit_tp.FusedAllReduce()
+            for j, (nm, n, k, kind) in enumerate(shard):
+                if kind == "row":
+                    fused._context(n, dev, j)
+            torch.cuda.synchronize()
+            allreduce_kind = "fused into the row-parallel GEMM (packets over NVLink peer memory)"
+        except Exception as exc:  # fall back to NCCL, loudly
+            if rank == 0:
+                print(f"[bench] fused all-reduce unavailable ({exc}); using NCCL", file=sys.stderr)
+            fused = None
     if world > 1 and want_ar == "peer":
         try:
             peer = petit_tp.PeerAllReduce()
@@ -255,7 +271,9 @@ def main():
     def layer_step(i, a_by_k=acts, collective=True):
         outs = []
         for j, (nm, n, k, kind, b, sp) in enumerate(layers[i % copies]):
-            if kind == "row" and world > 1 and collective and peer is not None:
+            if kind == "row" and world > 1 and collective and fused is not None:
+                c = fused.matmul(a_by_k[k], b, sp, gs, n, k, slot=j)
+            elif kind == "row" and world > 1 and collective and peer is not None:
                 buf = peer.buffer(m, n, torch.bfloat16, dev, j)
                 pk.ops.mul_nvfp4_a16_out(buf, a_by_k[k], b, sp, gs, m, n, k, -1)
                 c = peer.reduce(buf)
@@ -392,6 +410,9 @@ def main():
 
     def layer_step_out(i, a_by_k, outs):
         for j, (nm, n, k, kind, b, sp) in enumerate(layers[i % copies]):
+            if kind == "row" and world > 1 and fused is not None:
+                fused.matmul(a_by_k[k], b, sp, gs, n, k, out=outs[j], slot=j)
+                continue
             if kind == "row" and world > 1 and peer is not None:
                 buf = peer.buffer(m, n, torch.bfloat16, dev, j)
                 pk.ops.mul_nvfp4_a16_out(buf, a_by_k[k], b, sp, gs, m, n, k, -1)
@@ -512,6 +533,9 @@ def main():
         # our own kernels in the timed region: the GEMMs, plus the peer all-reduce launches
         "gpu_launches": args.steps * (len(shard) + (sum(1 for x in shard if x[3] == "row")
                                                     if (world > 1 and peer is not None) else 0)),
+        "launches_per_step": {"gemm": len(shard),
+                              "allreduce": (0 if (world == 1 or fused is not None)
+                                            else sum(1 for x in shard if x[3] == "row"))},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "frac_of_hbm_peak_layer_set": round(value / (hbm_peak * world), 4),
     }

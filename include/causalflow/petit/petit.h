@@ -213,6 +213,39 @@ int petit_allreduce_oneshot(void *out, const void *const *peer_bufs, void *const
                             void *epoch, int rank, int world, size_t numel, int dtype,
                             int end_barrier, petit_stream_t stream);
 
+/* Row-parallel (K-split) GEMM fused with the all-reduce of its output (SURVEY section 8 row f2;
+ * no reference counterpart): C = sum over ranks of (A_r x dequant(B_r)^T x global_scale), the
+ * same bits on every rank.  The CTA that finishes an output tile pushes its 16-bit partial into
+ * every peer's receive buffer over NVLink (self-validating {data, epoch} packets, no fence, no
+ * separate collective launch) and adds the peers' packets of that tile in rank order in fp32.
+ *   recv[r]: THIS process's mapping of rank r's receive buffer (symmetric / peer-mapped
+ *     memory, petit_fused_allreduce_recv_bytes(n) bytes, zeroed once before the first call
+ *     by its owner, then owned by these functions; recv[rank] is the local buffer);
+ *   state: local device words (petit_fused_allreduce_state_bytes(), zeroed once).
+ * Every rank calls it for every GEMM of the group, in the same order, with the same m <= 64,
+ * n and solution id (the call is CUDA-graph capturable; the call counter lives in `state`).
+ * A peer that does not deliver within PETIT_WATCHDOG_MS makes the waiting CTA go on without
+ * it; petit_fused_allreduce_status (synchronises the stream) then returns 1 + that rank,
+ * else 0 (-1: CUDA error). */
+typedef struct PetitFusedAllReduce {
+    int32_t world, rank;
+    void *recv[8];
+    void *state;
+} PetitFusedAllReduce;
+int petit_gemm_nvfp4_a16_allreduce(void *c, const void *a, const void *b, const void *scales,
+                                   const float *global_scale_dev, unsigned m, unsigned n,
+                                   unsigned k, const PetitSolutionHints *hints,
+                                   uint64_t solution_id, const PetitFusedAllReduce *ar,
+                                   petit_stream_t stream);
+int petit_gemm_mxfp4_a16_allreduce(void *c, const void *a, const void *b, const void *scales,
+                                   const float *global_scale_dev, unsigned m, unsigned n,
+                                   unsigned k, const PetitSolutionHints *hints,
+                                   uint64_t solution_id, const PetitFusedAllReduce *ar,
+                                   petit_stream_t stream);
+size_t petit_fused_allreduce_recv_bytes(unsigned n);
+size_t petit_fused_allreduce_state_bytes(void);
+int petit_fused_allreduce_status(const void *state, petit_stream_t stream);
+
 /* Stream-K workspace (library-owned, one per (device, stream), ~25 MB, created on the first
  * GEMM of a stream, at most 16 alive).  GEMMs that cut output tiles between CTAs let one CTA
  * wait for the partial sums of CTAs with higher block ids, which publish as soon as they are

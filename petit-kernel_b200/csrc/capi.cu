@@ -274,7 +274,17 @@ int get_context(cudaStream_t stream, Workspace *ws, int *num_sms) {
 int gemm_impl(void *c, const void *a, const void *b, const void *scales,
               const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
               const PetitSolutionHints *hints, uint64_t solution_id, bool force_mx,
-              cudaStream_t stream) {
+              cudaStream_t stream, const PetitFusedAllReduce *ar = nullptr) {
+    if (ar) {
+        // every rank must take part in every call: no early-out on empty shapes
+        if (m == 0 || n == 0 || k == 0 || m > gemm::kArMaxTokens) return PETIT_ERROR_PROBLEM_SHAPE;
+        if (ar->world < 2 || ar->world > (int)gemm::kArMaxWorld || ar->rank < 0 ||
+            ar->rank >= ar->world || !ar->state)
+            return PETIT_ERROR_PROBLEM_SHAPE;
+        for (int r = 0; r < ar->world; ++r)
+            if (!ar->recv[r] || (reinterpret_cast<uintptr_t>(ar->recv[r]) & 15))
+                return PETIT_ERROR_PROBLEM_SHAPE;
+    }
     if (m == 0 || n == 0 || k == 0) return PETIT_OK; // gemm_fp4_fp16_grid.cc:42-44
     if (!hints) return PETIT_ERROR_KERNEL_SHAPE;
     const bool is_mx = force_mx || hints->b_type == PETIT_DTYPE_MXFP4_E2M1;
@@ -334,6 +344,16 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
     args.n = n;
     args.k = k;
     args.trace = g_trace;
+    args.ar_world = 0;
+    args.ar_rank = 0;
+    args.ar_state = nullptr;
+    for (auto &p : args.ar_recv) p = nullptr;
+    if (ar) {
+        args.ar_world = (uint32_t)ar->world;
+        args.ar_rank = (uint32_t)ar->rank;
+        args.ar_state = static_cast<unsigned *>(ar->state);
+        for (int r = 0; r < ar->world; ++r) args.ar_recv[r] = static_cast<uint8_t *>(ar->recv[r]);
+    }
     {
         static const int pdl = [] {
             const char *e = std::getenv("PETIT_PDL");
@@ -395,6 +415,40 @@ int petit_gemm_mxfp4_a16(void *c, const void *a, const void *b, const void *scal
                          petit_stream_t stream) {
     return gemm_impl(c, a, b, scales, global_scale_dev, m, n, k, hints, solution_id, true,
                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+int petit_gemm_nvfp4_a16_allreduce(void *c, const void *a, const void *b, const void *scales,
+                                   const float *global_scale_dev, unsigned m, unsigned n,
+                                   unsigned k, const PetitSolutionHints *hints,
+                                   uint64_t solution_id, const PetitFusedAllReduce *ar,
+                                   petit_stream_t stream) {
+    if (!ar) return PETIT_ERROR_PROBLEM_SHAPE;
+    return gemm_impl(c, a, b, scales, global_scale_dev, m, n, k, hints, solution_id, false,
+                     reinterpret_cast<cudaStream_t>(stream), ar);
+}
+
+int petit_gemm_mxfp4_a16_allreduce(void *c, const void *a, const void *b, const void *scales,
+                                   const float *global_scale_dev, unsigned m, unsigned n,
+                                   unsigned k, const PetitSolutionHints *hints,
+                                   uint64_t solution_id, const PetitFusedAllReduce *ar,
+                                   petit_stream_t stream) {
+    if (!ar) return PETIT_ERROR_PROBLEM_SHAPE;
+    return gemm_impl(c, a, b, scales, global_scale_dev, m, n, k, hints, solution_id, true,
+                     reinterpret_cast<cudaStream_t>(stream), ar);
+}
+
+size_t petit_fused_allreduce_recv_bytes(unsigned n) { return gemm::ar_recv_bytes(n); }
+size_t petit_fused_allreduce_state_bytes(void) { return 4 * sizeof(unsigned); }
+
+int petit_fused_allreduce_status(const void *state, petit_stream_t stream) {
+    unsigned st = 0;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (!state ||
+        cudaMemcpyAsync(&st, static_cast<const unsigned *>(state) + 2, sizeof st,
+                        cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+        return -1;
+    return (int)st;
 }
 
 int petit_get_solutions(const PetitSolutionHints *hints, unsigned m, unsigned n, unsigned k,

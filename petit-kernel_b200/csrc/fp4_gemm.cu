@@ -747,6 +747,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         griddep_wait(); // global_scale, workspace and C may depend on the previous kernel
         float gs = *args.global_scale;
         gs *= epilogue_factor<MODE>(); // power of two folded out of the A operand
+        uint32_t ar_epoch = 0;
+        if (args.ar_world > 1)
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ar_epoch) : "l"(args.ar_state) : "memory");
+        const uint32_t sched_tiles_n = (args.n + kTileN - 1) / kTileN;
         uint32_t seg = 0;
         uint32_t out_buf = 0; // staging buffer the next 16-token group goes to
         for (uint32_t u = u_begin; u < u_end; ++seg) {
@@ -930,7 +934,100 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         for (int j = 0; j < 16; ++j) v[j] += x[j];
                     }
                 }
-                if (!PETIT_DBG(args.debug_flags, 64u)) {
+                if (args.ar_world > 1) {
+                    // ---- fused all-reduce (row-parallel GEMM): v[] holds this rank's partial.
+                    // Every rank finishes the same tile at about the same time (same shapes,
+                    // same schedule).  Push the 16-bit partial of this (tile, 16-token group)
+                    // to all peers as 16-byte packets {4 B data, epoch, 4 B data, epoch} --
+                    // each 8-byte half validates itself, so no fence or flag write is needed
+                    // -- then wait for the peers' packets in the local receive buffer and sum
+                    // all ranks' 16-bit partials in rank order in fp32 (identical on every
+                    // rank).  Two buffer parities alternate per call: a rank can only get one
+                    // call ahead of a peer (it needs that peer's packets to finish a call).
+                    const uint32_t epoch = ar_epoch + 1;
+                    const uint32_t n_slots = sched_tiles_n * (kArMaxTokens / 16);
+                    const uint32_t slot = g.n_tile * (kArMaxTokens / 16) + (m0 + (uint32_t)c0) / 16;
+                    const size_t src_stride = (size_t)n_slots * kArSlotBytes;
+                    const size_t par_off = (size_t)(epoch & 1) * kArMaxWorld * src_stride;
+                    const size_t my_off = par_off + (size_t)args.ar_rank * src_stride +
+                                          (size_t)slot * kArSlotBytes + row * 16;
+                    uint32_t own[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        own[j] = (uint32_t)to_bits16<C::kIsBf16>(v[2 * j] * gs) |
+                                 ((uint32_t)to_bits16<C::kIsBf16>(v[2 * j + 1] * gs) << 16);
+                    for (uint32_t p = 0; p < args.ar_world; ++p) {
+                        if (p == args.ar_rank) continue;
+                        uint8_t *dst = args.ar_recv[p] + my_off;
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd)
+                            asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(
+                                             dst + qd * 2048),
+                                         "r"(own[2 * qd]), "r"(epoch), "r"(own[2 * qd + 1])
+                                         : "memory");
+                    }
+                    float sum[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[j] = 0.f;
+                    uint32_t spins = 0;
+                    unsigned long long t_start = 0;
+                    bool gave_up = false;
+                    for (uint32_t p = 0; p < args.ar_world; ++p) {
+                        uint32_t d[8];
+                        if (p == args.ar_rank) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) d[j] = own[j];
+                        } else {
+                            const uint8_t *src = args.ar_recv[args.ar_rank] + par_off +
+                                                 (size_t)p * src_stride + (size_t)slot * kArSlotBytes +
+                                                 row * 16;
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd) {
+                                uint32_t x, fx, y, fy;
+                                for (;;) {
+                                    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=r"(x), "=r"(fx), "=r"(y), "=r"(fy)
+                                                 : "l"(src + qd * 2048)
+                                                 : "memory");
+                                    if ((fx == epoch && fy == epoch) || gave_up) break;
+                                    if ((++spins & 0x3ff) == 0) {
+                                        unsigned long long now;
+                                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                                        if (t_start == 0) t_start = now;
+                                        if (now - t_start > args.watchdog_ns) {
+                                            atomicExch(args.ar_state + 2, 1u + p);
+                                            gave_up = true;
+                                        }
+                                    }
+                                }
+                                d[2 * qd] = x;
+                                d[2 * qd + 1] = y;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (C::kIsBf16) {
+                                sum[2 * j] += __uint_as_float(d[j] << 16);
+                                sum[2 * j + 1] += __uint_as_float(d[j] & 0xffff0000u);
+                            } else {
+                                const __half2 h = *reinterpret_cast<const __half2 *>(&d[j]);
+                                sum[2 * j] += __low2float(h);
+                                sum[2 * j + 1] += __high2float(h);
+                            }
+                        }
+                    }
+                    uint16_t *stg = reinterpret_cast<uint16_t *>(team_stage + out_buf * C::kOutStageBytes);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) stg[j * kTileN + row] = to_bits16<C::kIsBf16>(sum[j]);
+                    fence_proxy_async();
+                    if (ew_tid == 0) bulk_wait_group_read<C::kOutBufs - 2>();
+                    named_bar_sync(team_bar, kNumEpilogueWarps * 32);
+                    if (ew_tid == 0) {
+                        tma_store_2d(&tmap_out, stg, (int)(g.n_tile * kTileN), (int)(m0 + c0));
+                        bulk_commit_group();
+                    }
+                    out_buf = out_buf == C::kOutBufs - 1 ? 0 : out_buf + 1;
+                } else if (!PETIT_DBG(args.debug_flags, 64u)) {
                     // [16 tokens][128 rows] 16-bit staging tile -> one TMA store; the tensor
                     // map clips tokens >= M and rows >= N.  Three buffers in rotation: the
                     // wait below (before the barrier) leaves only the previous group's store
@@ -981,6 +1078,15 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         __syncthreads();
     if (threadIdx.x == 0) trace_stamp(args, 8);
     if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
+    // fused all-reduce: the last CTA to exit advances the call epoch (every CTA read it at its
+    // start; the next launch reads it after this grid has completed)
+    if (args.ar_world > 1 && threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(args.ar_state + 1, 1u) == gridDim.x - 1) {
+            args.ar_state[1] = 0;
+            args.ar_state[0] += 1;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -29,7 +29,23 @@ struct GemmArgs {
     uint32_t use_pdl;       // launch with programmatic stream serialisation
     uint32_t skew_cycles;   // initial phase skew between k-slice warps (tuning knob)
     unsigned long long *trace; // optional [grid][16] globaltimer stamps (debug), else null
+    // Fused all-reduce of a row-parallel (K-split) GEMM over NVLink peer memory (ar_world > 1):
+    // the CTA that finishes an output tile pushes its 16-bit partial to every peer's receive
+    // buffer as self-validating {data, epoch} packets and sums the peers' packets of the same
+    // tile in rank order before it stores the tile (see fp4_gemm.cu, "fused all-reduce").
+    uint32_t ar_world, ar_rank;
+    uint8_t *ar_recv[8];       // rank p's receive buffer as mapped in this process
+    unsigned *ar_state;        // local device words: [0] epoch, [1] exited-CTA counter, [2] status
 };
+
+// Receive-buffer geometry of the fused all-reduce: [parity 2][source rank 8][slot][8 KB], one slot
+// per (n-tile, 16-token group); at most 64 tokens.
+constexpr unsigned kArMaxWorld = 8;
+constexpr unsigned kArMaxTokens = 64;
+constexpr unsigned kArSlotBytes = 8192;
+inline size_t ar_recv_bytes(unsigned n) {
+    return (size_t)2 * kArMaxWorld * ((n + 127) / 128) * (kArMaxTokens / 16) * kArSlotBytes;
+}
 
 size_t workspace_partials_bytes();
 size_t workspace_counters_bytes(); // kMaxTiles counters + the status word (last)

@@ -390,6 +390,49 @@ PYBIND11_MODULE(ops, m) {
           py::arg("out"), py::arg("a"), py::arg("b"), py::arg("s"), py::arg("global_scale"),
           py::arg("size_m"), py::arg("size_n"), py::arg("size_k"), py::arg("solution_id") = -1);
 
+    // extras: row-parallel GEMM fused with the all-reduce of its output (petit_tp.FusedAllReduce)
+    m.def(
+        "mul_fp4_a16_allreduce_out",
+        [](const torch::Tensor &out, const torch::Tensor &a, const torch::Tensor &b,
+           const torch::Tensor &s, const torch::Tensor &gs, int64_t sm, int64_t sn, int64_t sk,
+           int64_t sol, bool mx, const std::vector<int64_t> &recv_ptrs, const torch::Tensor &state,
+           int64_t rank) {
+            TORCH_CHECK(recv_ptrs.size() >= 2 && recv_ptrs.size() <= 8, "world must be 2..8");
+            TORCH_CHECK(state.is_cuda() && state.nbytes() >= petit_fused_allreduce_state_bytes(),
+                        "state buffer too small");
+            PetitDataType a_type = dtype_of(a);
+            check_gemm_operands(a, b, s, gs, sm, sn, sk, sn * sk / (mx ? 32 : 16));
+            c10::cuda::CUDAGuard guard(a.device());
+            torch::Tensor c = alloc_or_check_out(out, a, sm, sn);
+            PetitSolutionHints hints;
+            hints.a_type = a_type;
+            hints.b_type = mx ? PETIT_DTYPE_MXFP4_E2M1 : PETIT_DTYPE_FP4_E2M1;
+            hints.c_type = a_type;
+            hints.require_high_precision = 0;
+            PetitFusedAllReduce ar;
+            ar.world = (int32_t)recv_ptrs.size();
+            ar.rank = (int32_t)rank;
+            for (int r = 0; r < 8; ++r)
+                ar.recv[r] = r < ar.world ? reinterpret_cast<void *>(recv_ptrs[r]) : nullptr;
+            ar.state = state.data_ptr();
+            auto fn = mx ? petit_gemm_mxfp4_a16_allreduce : petit_gemm_nvfp4_a16_allreduce;
+            int err = fn(c.data_ptr(), a.data_ptr(), b.data_ptr(), s.data_ptr(), gs.data_ptr<float>(),
+                         sm, sn, sk, &hints, static_cast<uint64_t>(sol), &ar, stream_of(a));
+            check_status(err, sm, sn, sk, sol);
+            return c;
+        },
+        py::arg("out"), py::arg("a"), py::arg("b"), py::arg("s"), py::arg("global_scale"),
+        py::arg("size_m"), py::arg("size_n"), py::arg("size_k"), py::arg("solution_id"),
+        py::arg("mx"), py::arg("recv_ptrs"), py::arg("state"), py::arg("rank"));
+    m.def("fused_allreduce_recv_bytes",
+          [](int64_t n) { return (int64_t)petit_fused_allreduce_recv_bytes((unsigned)n); });
+    m.def("fused_allreduce_state_bytes", []() { return (int64_t)petit_fused_allreduce_state_bytes(); });
+    m.def("fused_allreduce_status", [](const torch::Tensor &state) {
+        c10::cuda::CUDAGuard guard(state.device());
+        return (int64_t)petit_fused_allreduce_status(
+            state.data_ptr(), at::cuda::getCurrentCUDAStream(state.device().index()).stream());
+    });
+
     // extras: tensor-parallel one-shot all-reduce over peer-mapped memory (petit_tp)
     m.def(
         "allreduce_oneshot",

@@ -176,6 +176,61 @@ class PeerAllReduce:
                                              eb, self.fenced)
 
 
+class FusedAllReduce:
+    """Row-parallel GEMM fused with the all-reduce of its output (csrc/fp4_gemm.cu, "fused
+    all-reduce"): `matmul()` launches ONE kernel per rank; the CTA that finishes an output tile
+    pushes its 16-bit partial into every peer's receive buffer over NVLink and sums the
+    peers' packets of that tile in rank order -- no collective launch, no barrier kernel.
+    One receive buffer (torch symmetric memory) per output width n; m <= 64."""
+
+    MAX_TOKENS = 64
+
+    def __init__(self, group=None):
+        import petit_kernel as pk  # CUDA extension; no fallback
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.pk = pk
+        self.symm_mem = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.ctx = {}
+
+    def _context(self, n: int, device, slot: int):
+        key = (n, slot)
+        if key not in self.ctx:
+            nbytes = self.pk.ops.fused_allreduce_recv_bytes(n)
+            raw = self.symm_mem.empty((nbytes,), dtype=torch.uint8, device=device)
+            raw.zero_()
+            hdl = self.symm_mem.rendezvous(raw, self.group.group_name)
+            state = torch.zeros(self.pk.ops.fused_allreduce_state_bytes() // 4, dtype=torch.int32,
+                                device=device)
+            torch.cuda.synchronize(device)
+            dist.barrier(self.group)  # every receive buffer is zero before anyone sends
+            ptrs = [int(hdl.buffer_ptrs[r]) for r in range(self.world)]
+            self.ctx[key] = (ptrs, state, raw, hdl)
+        return self.ctx[key]
+
+    def matmul(self, a, b, s, global_scale, n: int, k: int, fmt: str = "nvfp4",
+               out: "torch.Tensor | None" = None, slot: int = 0, solution_id: int = -1):
+        """sum over ranks of a_r @ dequant(b_r)^T * global_scale; `slot` separates layers of the
+        same width that are in flight in the same step."""
+        m = a.shape[0]
+        assert m <= self.MAX_TOKENS, "fused all-reduce handles at most 64 tokens"
+        ptrs, state = self._context(n, a.device, slot)[:2]
+        if out is None:
+            out = torch.empty((m, n), dtype=a.dtype, device=a.device)
+        return self.pk.ops.mul_fp4_a16_allreduce_out(out, a, b, s, global_scale, m, n, k,
+                                                     solution_id, fmt == "mxfp4", ptrs, state,
+                                                     self.rank)
+
+    def status(self) -> int:
+        worst = 0
+        for entry in self.ctx.values():
+            worst = max(worst, int(self.pk.ops.fused_allreduce_status(entry[1])))
+        return worst
+
+
 @dataclass
 class PackedLinear:
     """One FP4 linear layer resident on the current CUDA device."""
@@ -204,6 +259,9 @@ class PackedLinear:
         import petit_kernel as pk
 
         m = a.shape[0]
+        if self.kind == "row" and reduce and isinstance(symm, FusedAllReduce):
+            return symm.matmul(a, self.b, self.s, self.global_scale, self.n, self.k, self.fmt,
+                               slot=slot)
         if self.kind == "row" and reduce and isinstance(symm, PeerAllReduce):
             out = symm.buffer(m, self.n, a.dtype, a.device, slot)
             mul_out = (pk.ops.mul_nvfp4_a16_out if self.fmt == "nvfp4"

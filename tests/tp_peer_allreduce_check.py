@@ -53,6 +53,46 @@ def gemm_case(rank, world):
     assert par.status() == 0
 
 
+def fused_case(rank, world, iters):
+    """petit_tp.FusedAllReduce (GEMM + all-reduce in one kernel) against the GEMM followed by
+    ncclAllReduce, on shapes where tiles are whole and where stream-K splits them, for several
+    token counts, `iters` calls each (the epoch / buffer-parity protocol has to hold)."""
+    far = petit_tp.FusedAllReduce()
+    checked = []
+    for (m, n, k) in ((16, 1024, 2048 * world), (1, 8192, 1024 * world), (33, 2048, 512 * world),
+                      (64, 8192, 256 * world), (16, 8192, 3584 * world)):
+        a, q, s, gs = orc.make_nvfp4_case(m, n, k, 99 + m)
+        qs, ss = petit_tp.row_shard(q, s, world, rank)
+        a_s = petit_tp.row_shard_activation(a, world, rank).cuda()
+        ks = k // world
+        b = pk.repack_nvfp4(qs.cuda().contiguous().view(torch.int32), n, ks)
+        sp = pk.process_nvfp4_scales(ss.cuda().contiguous(), n, ks)
+        gsc = gs.cuda()
+        ref = pk.mul_nvfp4_a16(a_s, b, sp, gsc, m, n, ks, -1)
+        dist.all_reduce(ref)
+        bad = torch.zeros((), dtype=torch.int32, device="cuda")
+        first = None
+        for it in range(iters):
+            got = far.matmul(a_s, b, sp, gsc, n, ks)
+            if first is None:
+                first = got.clone()
+            bad += (got != first).any().to(torch.int32)
+        torch.cuda.synchronize()
+        assert bad.item() == 0, (m, n, k, "not reproducible across calls")
+        err = (first.float() - ref.float()).abs().max().item()
+        scale = ref.float().abs().max().item()
+        assert err <= scale * 2 ** -6, (m, n, k, err, scale)
+        gathered = [torch.empty_like(first) for _ in range(world)]
+        dist.all_gather(gathered, first)
+        assert all(torch.equal(gathered[0], x) for x in gathered), (m, n, k, "ranks differ")
+        if k <= 8192:
+            full = orc.nvfp4_gemm_ref_torch(a, q, s, gs)
+            assert orc.max_rel_err(first.float().cpu(), full) <= 1e-2
+        checked.append([m, n, k])
+    assert far.status() == 0
+    return checked
+
+
 def stress(rank, world, iters, end_barrier, fenced, m=16, n=8192):
     """Integer-valued bf16 data that changes every call: the exact sum is representable, so
     the peer kernel must match the closed form bit for bit (any stale 16-byte vector from a
@@ -86,6 +126,7 @@ def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     gemm_case(rank, world)
     res = {"world": world, "iters": iters, "modes": []}
+    res["fused_gemm_allreduce"] = {"shapes": fused_case(rank, world, max(50, iters // 20)), "ok": True}
     for end_barrier in (False, True):
         for fenced in (False, True):
             secs = stress(rank, world, iters, end_barrier, fenced)

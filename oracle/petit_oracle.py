@@ -33,8 +33,16 @@ What it restates (all citations into /root/reference):
 Pinning status: the NVFP4 functions are checked bit-for-bit against the
 reference's own Python oracle executed in the build container
 (``tests/golden/make_golden.py`` imports it from /root/reference and commits
-the vectors).  The MXFP4 GEMM reference is **parity unpinned by runnable code**
-(Quark absent); it is pinned only to the formulas cited above.
+the vectors).  The MXFP4 functions are pinned to implementations this repository
+did not write: AMD Quark itself is absent from the image, so
+``tests/golden/make_golden_mx.py`` builds the expectations of the reference test's
+recipe (``test_fp4_gemm_quark.py:71-87``) from torch's own OCP e8m0 dtype
+(``uint8.view(torch.float8_e8m0fnu)``) and compressed-tensors' e2m1 decoder
+(``unpack_fp4_from_uint8``), cross-checked against compressed-tensors'
+``decompress_mx_scale``; ``tests/test_oracle.py`` requires this module to reproduce
+``tests/golden/mxfp4_independent.npz`` bit for bit (dequantised weights incl. the
+exhaustive 16 x 237 table and the reference's scale-mixing pattern) and the GEMM
+vectors within one bf16 ulp.  What stays unpinned is only Quark's own code path.
 """
 from __future__ import annotations
 

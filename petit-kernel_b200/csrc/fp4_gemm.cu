@@ -966,55 +966,68 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                                          "r"(own[2 * qd]), "r"(epoch), "r"(own[2 * qd + 1])
                                          : "memory");
                     }
+                    // Receive: per packet row (4 tokens) the loads of ALL peers are in flight together
+                    // (one L2 round trip per attempt instead of one per peer and packet), then
+                    // the ranks' values are added in rank order.
                     float sum[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[j] = 0.f;
                     uint32_t spins = 0;
                     unsigned long long t_start = 0;
                     bool gave_up = false;
-                    for (uint32_t p = 0; p < args.ar_world; ++p) {
-                        uint32_t d[8];
-                        if (p == args.ar_rank) {
+                    const uint8_t *rbase = args.ar_recv[args.ar_rank] + par_off +
+                                           (size_t)slot * kArSlotBytes + row * 16;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) d[j] = own[j];
-                        } else {
-                            const uint8_t *src = args.ar_recv[args.ar_rank] + par_off +
-                                                 (size_t)p * src_stride + (size_t)slot * kArSlotBytes +
-                                                 row * 16;
+                    for (int qd = 0; qd < 4; ++qd) {
+                        uint32_t x[kArMaxWorld], y[kArMaxWorld];
+                        for (;;) {
+                            uint32_t fx[kArMaxWorld], fy[kArMaxWorld];
 #pragma unroll
-                            for (int qd = 0; qd < 4; ++qd) {
-                                uint32_t x, fx, y, fy;
-                                for (;;) {
+                            for (uint32_t p = 0; p < kArMaxWorld; ++p) {
+                                if (p < args.ar_world && p != args.ar_rank)
                                     asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                                 : "=r"(x), "=r"(fx), "=r"(y), "=r"(fy)
-                                                 : "l"(src + qd * 2048)
+                                                 : "=r"(x[p]), "=r"(fx[p]), "=r"(y[p]), "=r"(fy[p])
+                                                 : "l"(rbase + (size_t)p * src_stride + qd * 2048)
                                                  : "memory");
-                                    if ((fx == epoch && fy == epoch) || gave_up) break;
-                                    if ((++spins & 0x3ff) == 0) {
-                                        unsigned long long now;
-                                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                                        if (t_start == 0) t_start = now;
-                                        if (now - t_start > args.watchdog_ns) {
-                                            atomicExch(args.ar_state + 2, 1u + p);
-                                            gave_up = true;
-                                        }
-                                    }
-                                }
-                                d[2 * qd] = x;
-                                d[2 * qd + 1] = y;
                             }
-                        }
+                            bool ready = true;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (C::kIsBf16) {
-                                sum[2 * j] += __uint_as_float(d[j] << 16);
-                                sum[2 * j + 1] += __uint_as_float(d[j] & 0xffff0000u);
-                            } else {
-                                const __half2 h = *reinterpret_cast<const __half2 *>(&d[j]);
-                                sum[2 * j] += __low2float(h);
-                                sum[2 * j + 1] += __high2float(h);
+                            for (uint32_t p = 0; p < kArMaxWorld; ++p)
+                                if (p < args.ar_world && p != args.ar_rank)
+                                    ready = ready && fx[p] == epoch && fy[p] == epoch;
+                            if (ready || gave_up) break;
+                            if ((++spins & 0xff) == 0) {
+                                unsigned long long now;
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                                if (t_start == 0) t_start = now;
+                                if (now - t_start > args.watchdog_ns) {
+                                    atomicExch(args.ar_state + 2, 1u);
+                                    gave_up = true;
+                                }
                             }
                         }
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                        for (uint32_t p = 0; p < kArMaxWorld; ++p) {
+                            if (p >= args.ar_world) continue;
+                            const uint32_t lo = p == args.ar_rank ? own[2 * qd] : x[p];
+                            const uint32_t hi = p == args.ar_rank ? own[2 * qd + 1] : y[p];
+                            if (C::kIsBf16) {
+                                s0 += __uint_as_float(lo << 16);
+                                s1 += __uint_as_float(lo & 0xffff0000u);
+                                s2 += __uint_as_float(hi << 16);
+                                s3 += __uint_as_float(hi & 0xffff0000u);
+                            } else {
+                                const __half2 h0 = *reinterpret_cast<const __half2 *>(&lo);
+                                const __half2 h1 = *reinterpret_cast<const __half2 *>(&hi);
+                                s0 += __low2float(h0);
+                                s1 += __high2float(h0);
+                                s2 += __low2float(h1);
+                                s3 += __high2float(h1);
+                            }
+                        }
+                        sum[4 * qd] = s0;
+                        sum[4 * qd + 1] = s1;
+                        sum[4 * qd + 2] = s2;
+                        sum[4 * qd + 3] = s3;
                     }
                     uint16_t *stg = reinterpret_cast<uint16_t *>(team_stage + out_buf * C::kOutStageBytes);
 #pragma unroll

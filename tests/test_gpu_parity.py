@@ -67,6 +67,15 @@ def test_mxfp4_reference_cases(pk, m, n, k, seed):
     assert orc.max_rel_err(c, ref32) <= GEMM_TOL
     c_gold = from_bits16(golden("mxfp4_cases.npz")[f"m{m}_n{n}_k{k}_s{seed}_c"], torch.bfloat16)
     assert orc.max_rel_err(c, c_gold.float()) <= GEMM_TOL
+    # vectors built WITHOUT the oracle (torch e8m0 dtype x compressed-tensors e2m1 decoder,
+    # tests/golden/make_golden_mx.py): dequantised weights bit-exact, GEMM within tolerance
+    ind = golden("mxfp4_independent.npz")
+    tag = f"m{m}_n{n}_k{k}_s{seed}"
+    dense = pk.ops.dequant_dense(b, sp, 1.0, torch.bfloat16, n, k, True, True)
+    assert np.array_equal(bits16(dense), ind[f"{tag}_w"])
+    c_ind = from_bits16(ind[f"{tag}_c"], torch.bfloat16)
+    assert orc.max_rel_err(c, c_ind.float()) <= GEMM_TOL
+    torch.testing.assert_close(c.cpu().float() / scale, c_ind.float() / scale, rtol=2e-2, atol=2e-2)
 
 
 # ------------------------------------------------------------------ exhaustive dequant
@@ -108,6 +117,20 @@ def test_mxfp4_dequant_exhaustive_bit_exact(pk):
     assert orc.bits_equal_pm0(got_native, got_packed)
     with pytest.raises(RuntimeError):  # MXFP4 is bf16 only (gemm_fp4.h:19-21 -> -1)
         pk.ops.dequant_dense(b, sp, 1.0, torch.float16, n, k, True, True)
+    # the same two tables from implementations the oracle did not write
+    # (tests/golden/make_golden_mx.py): 16 codes x e8m0 1..237, and the mixing pattern slab
+    ind = golden("mxfp4_independent.npz")
+    sb = np.arange(1, 238, dtype=np.uint8)
+    n2, k2 = 128, 256 * 32          # 256 groups per row >= 237 scales
+    q2 = torch.from_numpy(np.repeat(((np.arange(n2) % 16).astype(np.uint8) * 0x11)[:, None], k2 // 2, axis=1).copy())
+    s2 = torch.from_numpy(np.tile(np.resize(sb, k2 // 32), (n2, 1)).copy())
+    b2, sp2 = pack_mxfp4(pk, q2, s2, n2, k2)
+    got = pk.ops.dequant_dense(b2, sp2, 1.0, torch.bfloat16, n2, k2, True, True)
+    assert np.array_equal(bits16(got[:16, :237 * 32:32]), ind["exhaustive_bf16_bits"])
+    qm, sm = torch.from_numpy(ind["mix_q"].copy()), torch.from_numpy(ind["mix_s"].copy())
+    bm, spm = pack_mxfp4(pk, qm, sm, 64, 512)
+    gm = pk.ops.dequant_dense(bm, spm, 1.0, torch.bfloat16, 64, 512, True, True)
+    assert np.array_equal(bits16(gm), ind["mix_w_bits"])
 
 
 def test_scale_edge_cases_documented(pk):

@@ -471,22 +471,36 @@ def main():
 
     # ---- roofline of the dominant kernel (the stream-K GEMM), per launch, live
     per_launch = []
-    for nm, n, k, kind, _, _ in layers[0]:
+    names0 = [x[0] for x in layers[0]]
+    for j, (nm, n, k, kind, _, _) in enumerate(layers[0]):
+        # row-parallel layers under TP: the launch that is timed is the fused GEMM + all-reduce
+        # (every rank runs the same loop, so the calls match up); the max over ranks is kept
+        with_ar = kind == "row" and world > 1 and fused is not None
+
+        def one(i):
+            b, sp = layers[i % copies][names0.index(nm)][4:6]
+            if with_ar:
+                fused.matmul(acts[k], b, sp, gs, n, k, slot=j)
+            else:
+                pk.mul_nvfp4_a16(acts[k], b, sp, gs, m, n, k, -1)
+
         for i in range(3):
-            b, sp = layers[i % copies][[x[0] for x in layers[0]].index(nm)][4:6]
-            pk.mul_nvfp4_a16(acts[k], b, sp, gs, m, n, k, -1)
-        torch.cuda.synchronize()
+            one(i)
+        sync()
         reps = 20
         e0.record()
         for i in range(reps):
-            b, sp = layers[i % copies][[x[0] for x in layers[0]].index(nm)][4:6]
-            pk.mul_nvfp4_a16(acts[k], b, sp, gs, m, n, k, -1)
+            one(i)
         e1.record()
         torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / reps * 1e3
+        tl = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device=dev)
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        us = tl.item()
         per_launch.append({"gemm": nm, "n": n, "k": k, "us": round(us, 2),
                            "gbs": round(algo_bytes(m, n, k) / us * 1e-3, 1),
-                           "frac_hbm": round(algo_bytes(m, n, k) / us * 1e-3 / hbm_peak, 4)})
+                           "frac_hbm": round(algo_bytes(m, n, k) / us * 1e-3 / hbm_peak, 4),
+                           "includes_allreduce": bool(with_ar)})
     shard_bytes = sum(algo_bytes(m, n, k) for _, n, k, _ in shard)
     avg_launch_us = sum(p["us"] for p in per_launch) / len(per_launch)
     achieved = (shard_bytes / len(shard)) / avg_launch_us * 1e-3

@@ -346,10 +346,17 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
     args.trace = g_trace;
     args.ar_world = 0;
     args.ar_rank = 0;
+    args.ar_two_shot = 0;
     args.ar_state = nullptr;
     for (auto &p : args.ar_recv) p = nullptr;
     if (ar) {
         args.ar_world = (uint32_t)ar->world;
+        // PETIT_AR_TWO_SHOT=0/1 overrides; must be the same on every rank
+        static const int two_shot_env = [] {
+            const char *e = std::getenv("PETIT_AR_TWO_SHOT");
+            return e ? std::atoi(e) : -1;
+        }();
+        args.ar_two_shot = two_shot_env >= 0 ? (uint32_t)(two_shot_env != 0) : (ar->world > 2 ? 1u : 0u);
         args.ar_rank = (uint32_t)ar->rank;
         args.ar_state = static_cast<unsigned *>(ar->state);
         for (int r = 0; r < ar->world; ++r) args.ar_recv[r] = static_cast<uint8_t *>(ar->recv[r]);

@@ -319,10 +319,13 @@ __device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
 // range but on adjacent n-tiles (2p, 2p+1).  Each CTA loads half of the token tile and
 // TMA-multicasts it into both CTAs' shared memory, halving the L2->SM activation
 // traffic that bounds the prefill kernel (measured 42.7 B/clk/SM, the L2 fabric cap).
-template <int MODE, int NTOK, int KS, bool CL>
+// AR = true: the instantiation whose epilogue also all-reduces the output over NVLink (separate
+// so that the plain GEMM's register allocation is untouched by the exchange code).
+template <int MODE, int NTOK, int KS, bool CL, bool AR = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
-                const __grid_constant__ CUtensorMap tmap_out, GemmArgs args) {
+                const __grid_constant__ CUtensorMap tmap_out,
+                const __grid_constant__ GemmArgs args) {
     using C = Cfg<MODE, NTOK, KS>;
     uint32_t cta_rank = 0;
     if (CL) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -748,7 +751,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         float gs = *args.global_scale;
         gs *= epilogue_factor<MODE>(); // power of two folded out of the A operand
         uint32_t ar_epoch = 0;
-        if (args.ar_world > 1)
+        if (AR)
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ar_epoch) : "l"(args.ar_state) : "memory");
         const uint32_t sched_tiles_n = (args.n + kTileN - 1) / kTileN;
         uint32_t seg = 0;
@@ -934,16 +937,21 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         for (int j = 0; j < 16; ++j) v[j] += x[j];
                     }
                 }
-                if (args.ar_world > 1) {
+                if (AR) {
                     // ---- fused all-reduce (row-parallel GEMM): v[] holds this rank's partial.
                     // Every rank finishes the same tile at about the same time (same shapes,
-                    // same schedule).  Push the 16-bit partial of this (tile, 16-token group)
-                    // to all peers as 16-byte packets {4 B data, epoch, 4 B data, epoch} --
-                    // each 8-byte half validates itself, so no fence or flag write is needed
-                    // -- then wait for the peers' packets in the local receive buffer and sum
-                    // all ranks' 16-bit partials in rank order in fp32 (identical on every
-                    // rank).  Two buffer parities alternate per call: a rank can only get one
-                    // call ahead of a peer (it needs that peer's packets to finish a call).
+                    // same schedule).  16-bit values travel as 16-byte packets {4 B data, epoch,
+                    // 4 B data, epoch} -- each 8-byte half validates itself, so no fence or flag
+                    // write is needed -- into the destination rank's receive buffer
+                    // [parity][source rank][slot]; ranks' values are always added in rank order
+                    // in fp32, so every rank ends up with the same bits.
+                    //  one-shot (world <= 2): push the partial to every peer, sum all partials.
+                    //  two-shot (larger worlds; 4x fewer NVLink bytes at 8 ranks, where the
+                    //    one-shot exchange measured 16 us per GEMM): tile t is reduced by rank
+                    //    t % world -- the others push their partial to it and wait for the
+                    //    finished tile, which it pushes back to everyone.
+                    // Two buffer parities alternate per call: a rank can only get one call ahead
+                    // of a peer (it needs that peer's packets to finish a call).
                     const uint32_t epoch = ar_epoch + 1;
                     const uint32_t n_slots = sched_tiles_n * (kArMaxTokens / 16);
                     const uint32_t slot = g.n_tile * (kArMaxTokens / 16) + (m0 + (uint32_t)c0) / 16;
@@ -951,48 +959,57 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     const size_t par_off = (size_t)(epoch & 1) * kArMaxWorld * src_stride;
                     const size_t my_off = par_off + (size_t)args.ar_rank * src_stride +
                                           (size_t)slot * kArSlotBytes + row * 16;
-                    uint32_t own[8];
+                    const uint8_t *my_recv = nullptr; // (constant indices: no local copy of the array)
+#pragma unroll
+                    for (uint32_t p = 0; p < kArMaxWorld; ++p)
+                        if (p == args.ar_rank) my_recv = args.ar_recv[p];
+                    const uint8_t *rbase = my_recv + par_off + (size_t)slot * kArSlotBytes + row * 16;
+                    const uint32_t all_mask = (1u << args.ar_world) - 1u;
+                    const uint32_t me_bit = 1u << args.ar_rank;
+                    const bool two_shot = args.ar_two_shot != 0;
+                    const uint32_t owner = two_shot ? g.n_tile % args.ar_world : args.ar_rank;
+                    uint32_t res[8]; // the tile's 16 tokens of this row as 16-bit pairs
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        own[j] = (uint32_t)to_bits16<C::kIsBf16>(v[2 * j] * gs) |
+                        res[j] = (uint32_t)to_bits16<C::kIsBf16>(v[2 * j] * gs) |
                                  ((uint32_t)to_bits16<C::kIsBf16>(v[2 * j + 1] * gs) << 16);
-                    for (uint32_t p = 0; p < args.ar_world; ++p) {
-                        if (p == args.ar_rank) continue;
-                        uint8_t *dst = args.ar_recv[p] + my_off;
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd)
-                            asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(
-                                             dst + qd * 2048),
-                                         "r"(own[2 * qd]), "r"(epoch), "r"(own[2 * qd + 1])
-                                         : "memory");
-                    }
-                    // Receive: per packet row (4 tokens) the loads of ALL peers are in flight together
-                    // (one L2 round trip per attempt instead of one per peer and packet), then
-                    // the ranks' values are added in rank order.
-                    float sum[16];
                     uint32_t spins = 0;
                     unsigned long long t_start = 0;
                     bool gave_up = false;
-                    const uint8_t *rbase = args.ar_recv[args.ar_rank] + par_off +
-                                           (size_t)slot * kArSlotBytes + row * 16;
+                    auto send = [&](uint32_t to_mask) {
 #pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        uint32_t x[kArMaxWorld], y[kArMaxWorld];
+                        for (uint32_t p = 0; p < kArMaxWorld; ++p) {
+                            if (!((to_mask >> p) & 1u)) continue;
+                            uint8_t *dst = args.ar_recv[p] + my_off;
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd)
+                                asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(
+                                                 dst + qd * 2048),
+                                             "r"(res[2 * qd]), "r"(epoch), "r"(res[2 * qd + 1])
+                                             : "memory");
+                        }
+                    };
+                    // wait for packet row qd of the (up to four) ranks base .. base + 3 that are in
+                    // from_mask; all loads of an attempt are in flight together (one L2 round
+                    // trip per attempt).  Four at a time keeps the epilogue warps inside their
+                    // 88 registers.
+                    auto wait_row4 = [&](uint32_t from_mask, uint32_t base, int qd, uint32_t (&x)[4],
+                                         uint32_t (&y)[4]) {
+                        const uint8_t *src = rbase + (size_t)base * src_stride + qd * 2048;
                         for (;;) {
-                            uint32_t fx[kArMaxWorld], fy[kArMaxWorld];
+                            uint32_t fx[4], fy[4];
 #pragma unroll
-                            for (uint32_t p = 0; p < kArMaxWorld; ++p) {
-                                if (p < args.ar_world && p != args.ar_rank)
+                            for (uint32_t i = 0; i < 4; ++i)
+                                if ((from_mask >> (base + i)) & 1u)
                                     asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                                 : "=r"(x[p]), "=r"(fx[p]), "=r"(y[p]), "=r"(fy[p])
-                                                 : "l"(rbase + (size_t)p * src_stride + qd * 2048)
+                                                 : "=r"(x[i]), "=r"(fx[i]), "=r"(y[i]), "=r"(fy[i])
+                                                 : "l"(src + (size_t)i * src_stride)
                                                  : "memory");
-                            }
                             bool ready = true;
 #pragma unroll
-                            for (uint32_t p = 0; p < kArMaxWorld; ++p)
-                                if (p < args.ar_world && p != args.ar_rank)
-                                    ready = ready && fx[p] == epoch && fy[p] == epoch;
+                            for (uint32_t i = 0; i < 4; ++i)
+                                if ((from_mask >> (base + i)) & 1u)
+                                    ready = ready && fx[i] == epoch && fy[i] == epoch;
                             if (ready || gave_up) break;
                             if ((++spins & 0xff) == 0) {
                                 unsigned long long now;
@@ -1004,34 +1021,67 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                                 }
                             }
                         }
-                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    };
+                    if (owner == args.ar_rank) {
+                        // reducer of this tile (every rank, for every tile, in one-shot mode)
+                        if (!two_shot) send(all_mask & ~me_bit);
+                        const uint32_t from = all_mask & ~me_bit;
 #pragma unroll
-                        for (uint32_t p = 0; p < kArMaxWorld; ++p) {
-                            if (p >= args.ar_world) continue;
-                            const uint32_t lo = p == args.ar_rank ? own[2 * qd] : x[p];
-                            const uint32_t hi = p == args.ar_rank ? own[2 * qd + 1] : y[p];
-                            if (C::kIsBf16) {
-                                s0 += __uint_as_float(lo << 16);
-                                s1 += __uint_as_float(lo & 0xffff0000u);
-                                s2 += __uint_as_float(hi << 16);
-                                s3 += __uint_as_float(hi & 0xffff0000u);
-                            } else {
-                                const __half2 h0 = *reinterpret_cast<const __half2 *>(&lo);
-                                const __half2 h1 = *reinterpret_cast<const __half2 *>(&hi);
-                                s0 += __low2float(h0);
-                                s1 += __high2float(h0);
-                                s2 += __low2float(h1);
-                                s3 += __high2float(h1);
+                        for (int qd = 0; qd < 4; ++qd) {
+                            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                            for (uint32_t base = 0; base < kArMaxWorld; base += 4) {
+                                if (base >= args.ar_world) continue;
+                                uint32_t x[4], y[4];
+                                if ((from >> base) & 0xfu) wait_row4(from, base, qd, x, y);
+#pragma unroll
+                                for (uint32_t i = 0; i < 4; ++i) {
+                                    const uint32_t p = base + i;
+                                    if (p >= args.ar_world) continue;
+                                    const uint32_t lo = p == args.ar_rank ? res[2 * qd] : x[i];
+                                    const uint32_t hi = p == args.ar_rank ? res[2 * qd + 1] : y[i];
+                                    if (C::kIsBf16) {
+                                        s0 += __uint_as_float(lo << 16);
+                                        s1 += __uint_as_float(lo & 0xffff0000u);
+                                        s2 += __uint_as_float(hi << 16);
+                                        s3 += __uint_as_float(hi & 0xffff0000u);
+                                    } else {
+                                        const __half2 h0 = *reinterpret_cast<const __half2 *>(&lo);
+                                        const __half2 h1 = *reinterpret_cast<const __half2 *>(&hi);
+                                        s0 += __low2float(h0);
+                                        s1 += __high2float(h0);
+                                        s2 += __low2float(h1);
+                                        s3 += __high2float(h1);
+                                    }
+                                }
                             }
+                            res[2 * qd] = (uint32_t)to_bits16<C::kIsBf16>(s0) |
+                                          ((uint32_t)to_bits16<C::kIsBf16>(s1) << 16);
+                            res[2 * qd + 1] = (uint32_t)to_bits16<C::kIsBf16>(s2) |
+                                              ((uint32_t)to_bits16<C::kIsBf16>(s3) << 16);
                         }
-                        sum[4 * qd] = s0;
-                        sum[4 * qd + 1] = s1;
-                        sum[4 * qd + 2] = s2;
-                        sum[4 * qd + 3] = s3;
+                        if (two_shot) send(all_mask & ~me_bit); // the finished tile
+                    } else {
+                        send(1u << owner); // my partial
+                        const uint32_t base = owner & ~3u;
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) {
+                            uint32_t x[4], y[4];
+                            wait_row4(1u << owner, base, qd, x, y);
+#pragma unroll
+                            for (uint32_t i = 0; i < 4; ++i)
+                                if (base + i == owner) {
+                                    res[2 * qd] = x[i];
+                                    res[2 * qd + 1] = y[i];
+                                }
+                        }
                     }
                     uint16_t *stg = reinterpret_cast<uint16_t *>(team_stage + out_buf * C::kOutStageBytes);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) stg[j * kTileN + row] = to_bits16<C::kIsBf16>(sum[j]);
+                    for (int j = 0; j < 8; ++j) {
+                        stg[(2 * j) * kTileN + row] = (uint16_t)(res[j] & 0xffffu);
+                        stg[(2 * j + 1) * kTileN + row] = (uint16_t)(res[j] >> 16);
+                    }
                     fence_proxy_async();
                     if (ew_tid == 0) bulk_wait_group_read<C::kOutBufs - 2>();
                     named_bar_sync(team_bar, kNumEpilogueWarps * 32);
@@ -1093,7 +1143,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
     if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
     // fused all-reduce: the last CTA to exit advances the call epoch (every CTA read it at its
     // start; the next launch reads it after this grid has completed)
-    if (args.ar_world > 1 && threadIdx.x == 0) {
+    if (AR && threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(args.ar_state + 1, 1u) == gridDim.x - 1) {
             args.ar_state[1] = 0;
@@ -1123,7 +1173,7 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int MODE, int NTOK, int KS, bool CL = false>
+template <int MODE, int NTOK, int KS, bool CL = false, bool AR = false>
 int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     using C = Cfg<MODE, NTOK, KS>;
     EncodeTiledFn encode = get_encode_fn();
@@ -1153,7 +1203,7 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return kLaunchCudaError;
 
     static std::atomic<bool> attr_set[64]; // per instantiation, per device (zero-initialised)
-    auto kern = fp4_gemm_kernel<MODE, NTOK, KS, CL>;
+    auto kern = fp4_gemm_kernel<MODE, NTOK, KS, CL, AR>;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return kLaunchCudaError;
     if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
@@ -1196,6 +1246,14 @@ template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
     // for the shared tile to matter
     const uint32_t n_tiles = (args.n + kTileN - 1) / kTileN;
     const bool cluster_ok = args.use_cluster && n_tiles % 2 == 0 && args.n % kTileN == 0;
+    if (args.ar_world > 1) { // fused all-reduce: decode tiles only (m <= 64, checked by the C ABI)
+        switch (ntok) {
+        case 16: return launch_variant<MODE, 16, 256, false, true>(args, num_sms, stream);
+        case 32: return launch_variant<MODE, 32, 256, false, true>(args, num_sms, stream);
+        case 64: return launch_variant<MODE, 64, 256, false, true>(args, num_sms, stream);
+        default: return kLaunchNoKernel;
+        }
+    }
     switch (ntok) {
     case 16: return launch_variant<MODE, 16, 256>(args, num_sms, stream);
     case 32: return launch_variant<MODE, 32, 256>(args, num_sms, stream);

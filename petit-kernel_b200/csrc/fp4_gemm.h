@@ -34,6 +34,7 @@ struct GemmArgs {
     // buffer as self-validating {data, epoch} packets and sums the peers' packets of the same
     // tile in rank order before it stores the tile (see fp4_gemm.cu, "fused all-reduce").
     uint32_t ar_world, ar_rank;
+    uint32_t ar_two_shot;      // 0: every rank sums every tile; 1: tile t is reduced by rank t % world
     uint8_t *ar_recv[8];       // rank p's receive buffer as mapped in this process
     unsigned *ar_state;        // local device words: [0] epoch, [1] exited-CTA counter, [2] status
 };

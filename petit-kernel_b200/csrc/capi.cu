@@ -356,7 +356,10 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
             const char *e = std::getenv("PETIT_AR_TWO_SHOT");
             return e ? std::atoi(e) : -1;
         }();
-        args.ar_two_shot = two_shot_env >= 0 ? (uint32_t)(two_shot_env != 0) : (ar->world > 2 ? 1u : 0u);
+        const bool can_two_shot = ar->world == 4 || ar->world == 8 || ar->world == 2;
+        args.ar_two_shot = !can_two_shot ? 0u
+                           : two_shot_env >= 0 ? (uint32_t)(two_shot_env != 0)
+                                               : (ar->world > 2 ? 1u : 0u);
         args.ar_rank = (uint32_t)ar->rank;
         args.ar_state = static_cast<unsigned *>(ar->state);
         for (int r = 0; r < ar->world; ++r) args.ar_recv[r] = static_cast<uint8_t *>(ar->recv[r]);

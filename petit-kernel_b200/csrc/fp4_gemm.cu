@@ -946,10 +946,15 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     // [parity][source rank][slot]; ranks' values are always added in rank order
                     // in fp32, so every rank ends up with the same bits.
                     //  one-shot (world <= 2): push the partial to every peer, sum all partials.
-                    //  two-shot (larger worlds; 4x fewer NVLink bytes at 8 ranks, where the
-                    //    one-shot exchange measured 16 us per GEMM): tile t is reduced by rank
-                    //    t % world -- the others push their partial to it and wait for the
-                    //    finished tile, which it pushes back to everyone.
+                    //  two-shot (world 4 or 8): reduce-scatter + all-gather inside every tile --
+                    //    rank r reduces rows [r * 128 / world, (r + 1) * 128 / world) of EVERY
+                    //    tile: a thread pushes its row's partial to the row's reducer and waits
+                    //    for the finished row, the reducer's threads sum the peers' partials and
+                    //    push the finished rows to everyone.  An SM sustains only ~10 GB/s of
+                    //    NVLink stores (measured: one CTA pushing a finished 8 KB tile to 7 peers
+                    //    took 5-10 us, the one-shot exchange 16 us per GEMM at 8 ranks), so the
+                    //    bytes have to be few (4x fewer than one-shot at 8 ranks) AND spread
+                    //    over all the CTAs that finish tiles.
                     // Two buffer parities alternate per call: a rank can only get one call ahead
                     // of a peer (it needs that peer's packets to finish a call).
                     const uint32_t epoch = ar_epoch + 1;
@@ -966,8 +971,8 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     const uint8_t *rbase = my_recv + par_off + (size_t)slot * kArSlotBytes + row * 16;
                     const uint32_t all_mask = (1u << args.ar_world) - 1u;
                     const uint32_t me_bit = 1u << args.ar_rank;
-                    const bool two_shot = args.ar_two_shot != 0;
-                    const uint32_t owner = two_shot ? g.n_tile % args.ar_world : args.ar_rank;
+                    const bool two_shot = args.ar_two_shot != 0; // host: only if 128 % world == 0
+                    const uint32_t owner = two_shot ? row / (kTileN / args.ar_world) : args.ar_rank;
                     uint32_t res[8]; // the tile's 16 tokens of this row as 16-bit pairs
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -1022,9 +1027,15 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                             }
                         }
                     };
+                    if (lead) trace_stamp(args, 11); // partial ready
+                    // phase A: partial -> the row's reducer (two-shot) / every peer (one-shot)
+                    if (!two_shot)
+                        send(all_mask & ~me_bit);
+                    else if (owner != args.ar_rank)
+                        send(1u << owner);
+                    if (lead) trace_stamp(args, 12);
                     if (owner == args.ar_rank) {
-                        // reducer of this tile (every rank, for every tile, in one-shot mode)
-                        if (!two_shot) send(all_mask & ~me_bit);
+                        // phase B: reducer of this row (every thread in one-shot mode)
                         const uint32_t from = all_mask & ~me_bit;
 #pragma unroll
                         for (int qd = 0; qd < 4; ++qd) {
@@ -1060,9 +1071,11 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                             res[2 * qd + 1] = (uint32_t)to_bits16<C::kIsBf16>(s2) |
                                               ((uint32_t)to_bits16<C::kIsBf16>(s3) << 16);
                         }
+                        if (lead) trace_stamp(args, 13); // all partials received and summed
                         if (two_shot) send(all_mask & ~me_bit); // the finished tile
+                        if (lead) trace_stamp(args, 14);
                     } else {
-                        send(1u << owner); // my partial
+                        // phase C: wait for the finished row from its reducer
                         const uint32_t base = owner & ~3u;
 #pragma unroll
                         for (int qd = 0; qd < 4; ++qd) {
@@ -1075,6 +1088,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                                     res[2 * qd + 1] = y[i];
                                 }
                         }
+                        if (lead) trace_stamp(args, 14); // finished tile received
                     }
                     uint16_t *stg = reinterpret_cast<uint16_t *>(team_stage + out_buf * C::kOutStageBytes);
 #pragma unroll

@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--m", type=int, default=16)
     ap.add_argument("--no-details", action="store_true")
+    ap.add_argument("--no-competitors", action="store_true",
+                    help="skip the cuBLAS / vLLM Marlin comparator rows of `details`")
     ap.add_argument("--graph", action="store_true",
                     help="replay one captured CUDA graph per layer step instead of eager launches")
     args = ap.parse_args()
@@ -520,6 +522,42 @@ def main():
                 "peak_source": peak_src, "kernel": "fp4_gemm_kernel<nvfp4,bf16,tok16> (stream-K tcgen05)",
                 "per_launch": per_launch}
 
+    # ---- TP only: the same sharded layer step at the other ends of config 5's M range
+    tp_m_sweep = None
+    if world > 1:
+        tp_m_sweep = []
+        for mm in (1, 64):
+            acts_mm = {k: torch.randn((mm, k), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+                       for k in acts}
+
+            def step_mm(i):
+                for j, (nm, n, k, kind, b, sp) in enumerate(layers[i % copies]):
+                    if kind == "row" and fused is not None:
+                        fused.matmul(acts_mm[k], b, sp, gs, n, k, slot=j)
+                    else:
+                        c = pk.mul_nvfp4_a16(acts_mm[k], b, sp, gs, mm, n, k, -1)
+                        if kind == "row":
+                            if peer is not None:
+                                buf = peer.buffer(mm, n, torch.bfloat16, dev, 8 + j)
+                                buf.copy_(c)
+                                peer.reduce(buf)
+                            else:
+                                dist.all_reduce(c)
+
+            for i in range(5):
+                step_mm(i)
+            sync()
+            e0.record()
+            for i in range(100):
+                step_mm(i)
+            e1.record()
+            sync()
+            tm = torch.tensor([e0.elapsed_time(e1) / 100], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            by = sum(algo_bytes(mm, n, k) for _, n, k, _ in LAYER)
+            tp_m_sweep.append({"m": mm, "us_per_step": round(tm.item() * 1e3, 2),
+                               "gbs": round(by / (tm.item() * 1e-3) / 1e9, 1)})
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -527,7 +565,8 @@ def main():
 
     details = None
     if world == 1 and not args.no_details:
-        details = sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak)
+        details = sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak,
+                                with_competitors=not args.no_competitors)
 
     torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1
     cores = torch.get_num_threads()
@@ -555,6 +594,8 @@ def main():
     }
     if tp_check is not None:
         out["tp_check"] = tp_check
+    if tp_m_sweep is not None:
+        out["tp_m_sweep"] = tp_m_sweep
     if details:
         out["details"] = details
     print(json.dumps(out))
@@ -562,55 +603,158 @@ def main():
         dist.destroy_process_group()
 
 
-def sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak):
-    """BASELINE metric in full: us / GB/s / % HBM at M = 1..16 (NVFP4 + MXFP4) and
-    TFLOPS / % peak at M >= 1024, per shape.  Outside the headline timed region."""
+def _timed(fn, reps, e0, e1):
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+def competitors(pk, layers, copies, gs, dev, hbm_peak, tf_peak):
+    """Same-box library comparators (the role of the reference bench's
+    hipBLASLt backend, tools/benchmarks/matmul/rocm/matmul_hipblaslt.cc:220-263), same CUDA
+    event method and weight rotation as the rest of this file:
+      * cuBLAS bf16 (torch.matmul) on weights dequantised ahead of time -- 4x the weight bytes;
+      * vLLM 0.22's Marlin FP4 W4A16 kernel (mma.sync path) on the same NVFP4 tensors.
+    Reported per shape and M; `vs_ours` = their us / our us on the same box."""
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    res = {"decode_nvfp4_bf16": [], "prefill_nvfp4_bf16": [], "decode_mxfp4_bf16": []}
+    g = torch.Generator(device=dev).manual_seed(11)
+    out = {"cublas_bf16_dense": [], "vllm_marlin_fp4": [], "notes": []}
+    names = [x[0] for x in layers[0]]
+    ms = (1, 16, 64, 1024)
+    ours = {}
+    for nm, n, k, _, _, _ in layers[0]:
+        idx = names.index(nm)
+        for m in ms:
+            a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)
+            ours[(nm, m)] = _timed(lambda i: pk.mul_nvfp4_a16(a, layers[i % copies][idx][4],
+                                                               layers[i % copies][idx][5], gs, m, n, k, -1),
+                                   20 if m <= 64 else 5, e0, e1)
+    # ---- cuBLAS bf16 on pre-dequantised weights (distinct dense copies > L2)
+    for nm, n, k, _, _, _ in layers[0]:
+        idx = names.index(nm)
+        ncopy = max(2, min(copies, int(400e6 // (n * k * 2)) + 1))
+        dense = [pk.ops.dequant_dense(layers[c % copies][idx][4], layers[c % copies][idx][5], 1.0,
+                                      torch.bfloat16, n, k, False, True) for c in range(ncopy)]
+        for m in ms:
+            a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)
+            us = _timed(lambda i: torch.matmul(a, dense[i % ncopy].t()), 20 if m <= 64 else 5, e0, e1)
+            by = 2 * n * k + 2 * m * k + 2 * m * n
+            out["cublas_bf16_dense"].append({
+                "gemm": nm, "m": m, "us": round(us, 2), "ours_us": round(ours[(nm, m)], 2),
+                "vs_ours": round(us / ours[(nm, m)], 2), "bytes": by,
+                "frac_hbm_own_bytes": round(by / us * 1e-3 / hbm_peak, 3),
+                "tflops": round(2.0 * m * n * k / us * 1e-6, 1)})
+        del dense
+        torch.cuda.empty_cache()
+    # ---- vLLM Marlin FP4 (W4A16, NVFP4 weights)
+    try:
+        from vllm.model_executor.layers.quantization.utils import marlin_utils_fp4 as mfp4
+
+        class _L(torch.nn.Module):
+            pass
+
+        for nm, n, k, _, _, _ in layers[0]:
+            lays = []
+            for c in range(2):
+                q = torch.randint(0, 256, (n, k // 2), generator=g, dtype=torch.uint8, device=dev)
+                sc = (torch.rand((n, k // 16), generator=g, device=dev) * 3.5 + 0.25).to(torch.float8_e4m3fn)
+                lay = _L()
+                lay.output_size_per_partition, lay.input_size_per_partition = n, k
+                lay.params_dtype = torch.bfloat16
+                lay.weight = torch.nn.Parameter(q, requires_grad=False)
+                lay.weight_scale = torch.nn.Parameter(sc, requires_grad=False)
+                lay.weight_global_scale = torch.nn.Parameter(torch.ones(1, device=dev), requires_grad=False)
+                mfp4.prepare_fp4_layer_for_marlin(lay)
+                lays.append(lay)
+            for m in ms:
+                a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)
+
+                def run(i, lays=lays, a=a, n=n, k=k):
+                    lay = lays[i % 2]
+                    return mfp4.apply_fp4_marlin_linear(a, lay.weight, lay.weight_scale,
+                                                        lay.weight_global_scale, lay.workspace, n, k)
+
+                us = _timed(run, 20 if m <= 64 else 5, e0, e1)
+                out["vllm_marlin_fp4"].append({
+                    "gemm": nm, "m": m, "us": round(us, 2), "ours_us": round(ours[(nm, m)], 2),
+                    "vs_ours": round(us / ours[(nm, m)], 2),
+                    "frac_hbm": round(algo_bytes(m, n, k) / us * 1e-3 / hbm_peak, 3),
+                    "tflops": round(2.0 * m * n * k / us * 1e-6, 1)})
+            del lays
+            torch.cuda.empty_cache()
+        out["notes"].append("vLLM Marlin: 2 weight copies per shape (qkv / o fit in L2 between reuses: "
+                            "an upper bound on its speed for those two)")
+    except Exception as exc:  # not fatal: the comparator is a library outside this repo
+        out["vllm_marlin_fp4"] = None
+        out["notes"].append(f"vLLM Marlin FP4 unavailable on this box: {type(exc).__name__}: {str(exc)[:200]}")
+    return out
+
+
+def sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak, with_competitors=True):
+    """BASELINE metric in full: us / GB/s / % HBM at M = 1..16 (NVFP4 bf16 + fp16, MXFP4), the
+    mid-M points, TFLOPS / % peak at M = 256..8192, per shape.  Outside the headline timed region."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = {"decode_nvfp4_bf16": [], "decode_nvfp4_fp16": [], "decode_mxfp4_bf16": [],
+           "mid_m_nvfp4_bf16": [], "prefill_nvfp4_bf16": []}
     g = torch.Generator(device=dev).manual_seed(7)
     names = [x[0] for x in layers[0]]
 
-    def timed(fn, reps):
-        for i in range(3):
-            fn(i)
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(reps):
-            fn(i)
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps * 1e3
+    def hbm_row(nm, m, us, group=16):
+        n, k = [(x[1], x[2]) for x in layers[0] if x[0] == nm][0]
+        by = algo_bytes(m, n, k, group)
+        return {"gemm": nm, "m": m, "us": round(us, 2), "gbs": round(by / us * 1e-3),
+                "frac_hbm": round(by / us * 1e-3 / hbm_peak, 3)}
 
     for nm, n, k, _, _, _ in layers[0]:
         idx = names.index(nm)
         for m in (1, 4, 8, 16):
             a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)
-            us = timed(lambda i: pk.mul_nvfp4_a16(a, layers[i % copies][idx][4], layers[i % copies][idx][5],
-                                                  gs, m, n, k, -1), 20)
-            by = algo_bytes(m, n, k)
-            res["decode_nvfp4_bf16"].append({"gemm": nm, "m": m, "us": round(us, 2),
-                                             "gbs": round(by / us * 1e-3), "frac_hbm": round(by / us * 1e-3 / hbm_peak, 3)})
-    # MXFP4 (config 3) on the two mid-sized shapes
-    for nm, n, k in (("qkv", 10240, 8192), ("down", 8192, 28672)):
+            us = _timed(lambda i: pk.mul_nvfp4_a16(a, layers[i % copies][idx][4], layers[i % copies][idx][5],
+                                                   gs, m, n, k, -1), 20, e0, e1)
+            res["decode_nvfp4_bf16"].append(hbm_row(nm, m, us))
+        for m in (32, 64):
+            a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)
+            us = _timed(lambda i: pk.mul_nvfp4_a16(a, layers[i % copies][idx][4], layers[i % copies][idx][5],
+                                                   gs, m, n, k, -1), 20, e0, e1)
+            row = hbm_row(nm, m, us)
+            row["tflops"] = round(2.0 * m * n * k / us * 1e-6, 1)
+            res["mid_m_nvfp4_bf16"].append(row)
+        a = torch.randn((16, k), generator=g, device=dev).to(torch.float16)
+        us = _timed(lambda i: pk.mul_nvfp4_a16(a, layers[i % copies][idx][4], layers[i % copies][idx][5],
+                                               gs, 16, n, k, -1), 20, e0, e1)
+        res["decode_nvfp4_fp16"].append(hbm_row(nm, 16, us))
+    # MXFP4 (config 3): all four shapes, M = 1, 4, 8, 16
+    for nm, n, k, _, _, _ in layers[0]:
+        ncopy = max(2, int(300e6 // (n * k // 2 + n * k // 32)) + 1)
         packs = []
-        for _ in range(3):
+        for _ in range(ncopy):
             q = torch.randint(0, 256, (n, k // 2), generator=g, dtype=torch.uint8, device=dev)
             s = torch.randint(108, 125, (n, k // 32), generator=g, dtype=torch.uint8, device=dev)  # 2^-19..2^-3, typical of MX weights
             packs.append((pk.repack_mxfp4(q.view(torch.int32), n, k), pk.process_mxfp4_scales(s, n, k)))
-        for m in (1, 16):
+            del q, s
+        for m in (1, 4, 8, 16):
             a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)
-            us = timed(lambda i: pk.mul_mxfp4_a16(a, packs[i % 3][0], packs[i % 3][1], gs, m, n, k, -1), 20)
-            by = algo_bytes(m, n, k, 32)
-            res["decode_mxfp4_bf16"].append({"gemm": nm, "m": m, "us": round(us, 2), "gbs": round(by / us * 1e-3),
-                                             "frac_hbm": round(by / us * 1e-3 / hbm_peak, 3)})
+            us = _timed(lambda i: pk.mul_mxfp4_a16(a, packs[i % ncopy][0], packs[i % ncopy][1], gs, m, n, k, -1),
+                        20, e0, e1)
+            res["decode_mxfp4_bf16"].append(hbm_row(nm, m, us, 32))
+        del packs
+        torch.cuda.empty_cache()
+    if with_competitors:
+        res["competitors"] = competitors(pk, layers, copies, gs, dev, hbm_peak, tf_peak)
     # prefill last: it power-caps the part, and the decode kernels are issue-bound
     # (clock-sensitive)
     for nm, n, k, _, _, _ in layers[0]:
         idx = names.index(nm)
-        for m in (1024, 4096):
+        for m in (256, 512, 1024, 2048, 4096, 8192):
             a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)
-            us = timed(lambda i: pk.mul_nvfp4_a16(a, layers[i % copies][idx][4], layers[i % copies][idx][5],
-                                                  gs, m, n, k, -1), 5)
+            us = _timed(lambda i: pk.mul_nvfp4_a16(a, layers[i % copies][idx][4], layers[i % copies][idx][5],
+                                                   gs, m, n, k, -1), 5, e0, e1)
             tf = 2.0 * m * n * k / us * 1e-6
             res["prefill_nvfp4_bf16"].append({"gemm": nm, "m": m, "us": round(us, 1),
                                               "tflops": round(tf, 1), "frac_bf16_peak": round(tf / tf_peak, 3)})

@@ -745,12 +745,14 @@ def sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak, with_competito
             res["decode_mxfp4_bf16"].append(hbm_row(nm, m, us, 32))
         del packs
         torch.cuda.empty_cache()
-    if with_competitors:
-        res["competitors"] = competitors(pk, layers, copies, gs, dev, hbm_peak, tf_peak)
-    # prefill last: it power-caps the part, and the decode kernels are issue-bound
-    # (clock-sensitive)
+    # prefill after the decode rows: it power-caps the part, and the decode kernels are
+    # issue-bound (clock-sensitive).  The denominator is the BURST bf16 peak, so every shape
+    # starts from an idle part (1 s pause): back to back the sweep runs into the 1 kW power cap
+    # and measures the sustained clock instead (down M=2048: 58 % vs 83 % in isolation).
     for nm, n, k, _, _, _ in layers[0]:
         idx = names.index(nm)
+        torch.cuda.synchronize()
+        time.sleep(1.0)
         for m in (256, 512, 1024, 2048, 4096, 8192):
             a = torch.randn((m, k), generator=g, device=dev).to(torch.bfloat16)
             us = _timed(lambda i: pk.mul_nvfp4_a16(a, layers[i % copies][idx][4], layers[i % copies][idx][5],
@@ -758,6 +760,9 @@ def sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak, with_competito
             tf = 2.0 * m * n * k / us * 1e-6
             res["prefill_nvfp4_bf16"].append({"gemm": nm, "m": m, "us": round(us, 1),
                                               "tflops": round(tf, 1), "frac_bf16_peak": round(tf / tf_peak, 3)})
+    if with_competitors:
+        time.sleep(1.0)
+        res["competitors"] = competitors(pk, layers, copies, gs, dev, hbm_peak, tf_peak)
     return res
 
 

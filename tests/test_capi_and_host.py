@@ -11,7 +11,7 @@ import subprocess
 import pytest
 import torch
 
-from helpers import HEADER, ROOT, ensure_built
+from helpers import HEADER, LIB_PATH, ROOT, ensure_built
 
 
 @pytest.fixture(scope="module")
@@ -340,3 +340,27 @@ def test_percta_trace_tool_summarises_the_committed_traces():
     for gemm in ("qkv", "o", "gate_up", "down"):
         assert f"== {gemm} launch 1, 148 CTAs" in out
     assert out.count("griddep_wait_done") == 4 and out.count("late cta") == 24
+
+
+def _build_compat_user(tmp_path):
+    exe = os.path.join(str(tmp_path), "compat_user")
+    lib_dir = os.path.dirname(LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           "-I", "/usr/local/cuda/include",
+                           os.path.join(ROOT, "tests", "native", "compat_user.cc"), "-o", exe,
+                           "-L", lib_dir, "-lpetit_b200", f"-Wl,-rpath,{lib_dir}",
+                           "-L", "/usr/local/cuda/lib64", "-lcudart"])
+    return exe
+
+
+def test_cpp_source_compat_header_compiles_and_host_calls_work(tmp_path):
+    """include/causalflow/petit/gemm_compat.h: a unit written against the reference's C++
+    interface (namespace causalflow::petit::rocm::quantization[::fp4], SolutionId,
+    PetitSolutionHints, hal::GetPlatform; gemm.h:6-146, gemm_fp4.h:11-21, hal/device.h:8-34)
+    compiles, links against libpetit_b200.so and its host-only calls behave like the
+    reference's (enumeration, m == 0 no-op, -1 for an unsupported b_type)."""
+    ensure_built()
+    exe = _build_compat_user(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "compat host checks ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+

@@ -497,6 +497,16 @@ def test_native_selftest_binary(pk):
     assert r.returncode == 0, r.stdout[-2000:]
 
 
+def test_cpp_source_compat_header_runs_a_gemm(pk, tmp_path):
+    """The reference-style C++ unit (tests/native/compat_user.cc over gemm_compat.h) repacks and
+    multiplies on the GPU through the namespace-compatible shim and the hal::Device object."""
+    from test_capi_and_host import _build_compat_user
+
+    exe = _build_compat_user(tmp_path)
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "compat gpu GEMM ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
 def test_bench_matmul_cli_tune(pk):
     """`bench_matmul -algo tune` lists every solution, prints the reference's result line
     for the fastest five, and a printed id can be fed back through -algo."""

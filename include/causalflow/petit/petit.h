@@ -242,6 +242,32 @@ int petit_gemm_mxfp4_a16_allreduce(void *c, const void *a, const void *b, const 
                                    unsigned k, const PetitSolutionHints *hints,
                                    uint64_t solution_id, const PetitFusedAllReduce *ar,
                                    petit_stream_t stream);
+/* Fused epilogue (extends WriteResult, qgemm.cuh:95-192): what the
+ * callers of the reference do right after the GEMM -- `output.add_(bias)`, the residual add --
+ * happens on the fp32 accumulator before the single rounding to the output type:
+ *     C[m, n] = round(acc[m, n] * global_scale + bias[n] + residual[m, n])
+ * bias: [n], residual: [m, n] row-major, both in the output type, either may be NULL;
+ * residual may alias c.  activation must be PETIT_ACT_NONE (reserved).  `ar` may be NULL (plain
+ * GEMM) or a fused all-reduce context; then bias / residual are added to THIS rank's partial,
+ * i.e. a row-parallel layer passes them on one rank only. */
+#define PETIT_ACT_NONE 0
+typedef struct PetitEpilogue {
+    const void *bias;
+    const void *residual;
+    int32_t activation;
+    int32_t reserved;
+} PetitEpilogue;
+int petit_gemm_nvfp4_a16_ex(void *c, const void *a, const void *b, const void *scales,
+                            const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
+                            const PetitSolutionHints *hints, uint64_t solution_id,
+                            const PetitEpilogue *epilogue, const PetitFusedAllReduce *ar,
+                            petit_stream_t stream);
+int petit_gemm_mxfp4_a16_ex(void *c, const void *a, const void *b, const void *scales,
+                            const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
+                            const PetitSolutionHints *hints, uint64_t solution_id,
+                            const PetitEpilogue *epilogue, const PetitFusedAllReduce *ar,
+                            petit_stream_t stream);
+
 size_t petit_fused_allreduce_recv_bytes(unsigned n);
 size_t petit_fused_allreduce_state_bytes(void);
 int petit_fused_allreduce_status(const void *state, petit_stream_t stream);

@@ -274,7 +274,8 @@ int get_context(cudaStream_t stream, Workspace *ws, int *num_sms) {
 int gemm_impl(void *c, const void *a, const void *b, const void *scales,
               const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
               const PetitSolutionHints *hints, uint64_t solution_id, bool force_mx,
-              cudaStream_t stream, const PetitFusedAllReduce *ar = nullptr) {
+              cudaStream_t stream, const PetitFusedAllReduce *ar = nullptr,
+              const PetitEpilogue *epi = nullptr) {
     if (ar) {
         // every rank must take part in every call: no early-out on empty shapes
         if (m == 0 || n == 0 || k == 0 || m > gemm::kArMaxTokens) return PETIT_ERROR_PROBLEM_SHAPE;
@@ -344,6 +345,16 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
     args.n = n;
     args.k = k;
     args.trace = g_trace;
+    args.bias = nullptr;
+    args.residual = nullptr;
+    if (epi) {
+        if (epi->activation != PETIT_ACT_NONE) return PETIT_ERROR_KERNEL_SHAPE;
+        // 2-byte elements, read with scalar loads: natural alignment is enough
+        if (((reinterpret_cast<uintptr_t>(epi->bias) | reinterpret_cast<uintptr_t>(epi->residual)) & 1) != 0)
+            return PETIT_ERROR_PROBLEM_SHAPE;
+        args.bias = epi->bias;
+        args.residual = epi->residual;
+    }
     args.ar_world = 0;
     args.ar_rank = 0;
     args.ar_two_shot = 0;
@@ -445,6 +456,24 @@ int petit_gemm_mxfp4_a16_allreduce(void *c, const void *a, const void *b, const 
     if (!ar) return PETIT_ERROR_PROBLEM_SHAPE;
     return gemm_impl(c, a, b, scales, global_scale_dev, m, n, k, hints, solution_id, true,
                      reinterpret_cast<cudaStream_t>(stream), ar);
+}
+
+int petit_gemm_nvfp4_a16_ex(void *c, const void *a, const void *b, const void *scales,
+                            const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
+                            const PetitSolutionHints *hints, uint64_t solution_id,
+                            const PetitEpilogue *epilogue, const PetitFusedAllReduce *ar,
+                            petit_stream_t stream) {
+    return gemm_impl(c, a, b, scales, global_scale_dev, m, n, k, hints, solution_id, false,
+                     reinterpret_cast<cudaStream_t>(stream), ar, epilogue);
+}
+
+int petit_gemm_mxfp4_a16_ex(void *c, const void *a, const void *b, const void *scales,
+                            const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
+                            const PetitSolutionHints *hints, uint64_t solution_id,
+                            const PetitEpilogue *epilogue, const PetitFusedAllReduce *ar,
+                            petit_stream_t stream) {
+    return gemm_impl(c, a, b, scales, global_scale_dev, m, n, k, hints, solution_id, true,
+                     reinterpret_cast<cudaStream_t>(stream), ar, epilogue);
 }
 
 size_t petit_fused_allreduce_recv_bytes(unsigned n) { return gemm::ar_recv_bytes(n); }

@@ -937,6 +937,35 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         for (int j = 0; j < 16; ++j) v[j] += x[j];
                     }
                 }
+                // Fused epilogue terms (extends WriteResult, qgemm.cuh:146-156): the final owner of
+                // a tile adds bias[n] and residual[m, n] in fp32 before the one rounding to the
+                // output type.  (Under the fused all-reduce they go into THIS rank's partial: a
+                // row-parallel layer passes them on one rank only, as frameworks do with bias.)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] *= gs;
+                if (args.bias != nullptr || args.residual != nullptr) {
+                    const uint32_t col = g.n_tile * kTileN + row;
+                    if (row < rows) {
+                        if (args.bias != nullptr) {
+                            const uint16_t bb = static_cast<const uint16_t *>(args.bias)[col];
+                            const float bv = C::kIsBf16 ? __uint_as_float((uint32_t)bb << 16)
+                                                        : __half2float(__ushort_as_half(bb));
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += bv;
+                        }
+                        if (args.residual != nullptr) {
+                            const uint16_t *rp = static_cast<const uint16_t *>(args.residual) +
+                                                 (size_t)(m0 + c0) * args.n + col;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if ((uint32_t)(c0 + j) < m_valid) {
+                                    const uint16_t rb = rp[(size_t)j * args.n];
+                                    v[j] += C::kIsBf16 ? __uint_as_float((uint32_t)rb << 16)
+                                                       : __half2float(__ushort_as_half(rb));
+                                }
+                        }
+                    }
+                }
                 if (AR) {
                     // ---- fused all-reduce (row-parallel GEMM): v[] holds this rank's partial.
                     // Every rank finishes the same tile at about the same time (same shapes,
@@ -976,8 +1005,8 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     uint32_t res[8]; // the tile's 16 tokens of this row as 16-bit pairs
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        res[j] = (uint32_t)to_bits16<C::kIsBf16>(v[2 * j] * gs) |
-                                 ((uint32_t)to_bits16<C::kIsBf16>(v[2 * j + 1] * gs) << 16);
+                        res[j] = (uint32_t)to_bits16<C::kIsBf16>(v[2 * j]) |
+                                 ((uint32_t)to_bits16<C::kIsBf16>(v[2 * j + 1]) << 16);
                     uint32_t spins = 0;
                     unsigned long long t_start = 0;
                     bool gave_up = false;
@@ -1111,7 +1140,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     // in flight, so the buffer the NEXT group fills is known to be drained.
                     uint16_t *stg = reinterpret_cast<uint16_t *>(team_stage + out_buf * C::kOutStageBytes);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) stg[j * kTileN + row] = to_bits16<C::kIsBf16>(v[j] * gs);
+                    for (int j = 0; j < 16; ++j) stg[j * kTileN + row] = to_bits16<C::kIsBf16>(v[j]);
                     if (!PETIT_DBG(args.debug_flags, 256u)) fence_proxy_async();
                     if (ew_tid == 0 && !PETIT_DBG(args.debug_flags, 128u))
                         bulk_wait_group_read<C::kOutBufs - 2>();

@@ -19,6 +19,8 @@ struct GemmArgs {
     const uint8_t *sc;      // packed scales
     const float *global_scale; // device pointer
     void *c;                // [m, n] 16-bit row-major
+    const void *bias;       // optional [n] in the output type: added in fp32 before rounding
+    const void *residual;   // optional [m, n] in the output type: added in fp32 before rounding
     float *ws_partials;     // stream-K partial tiles
     unsigned *ws_counters;  // per-tile arrival counters (zero between launches)
     unsigned *ws_status;    // sticky: != 0 once a split-tile reducer gave up waiting (watchdog)

@@ -390,6 +390,45 @@ PYBIND11_MODULE(ops, m) {
           py::arg("out"), py::arg("a"), py::arg("b"), py::arg("s"), py::arg("global_scale"),
           py::arg("size_m"), py::arg("size_n"), py::arg("size_k"), py::arg("solution_id") = -1);
 
+    // extras: GEMM with the fused epilogue (bias / residual added in fp32 before the rounding)
+    m.def(
+        "mul_fp4_a16_ex_out",
+        [](const c10::optional<torch::Tensor> &out, const torch::Tensor &a, const torch::Tensor &b,
+           const torch::Tensor &s, const torch::Tensor &gs, int64_t sm, int64_t sn, int64_t sk,
+           int64_t sol, bool mx, const c10::optional<torch::Tensor> &bias,
+           const c10::optional<torch::Tensor> &residual) {
+            PetitDataType a_type = dtype_of(a);
+            check_gemm_operands(a, b, s, gs, sm, sn, sk, sn * sk / (mx ? 32 : 16));
+            c10::cuda::CUDAGuard guard(a.device());
+            torch::Tensor c = alloc_or_check_out(out, a, sm, sn);
+            PetitEpilogue epi = {nullptr, nullptr, PETIT_ACT_NONE, 0};
+            if (bias.has_value()) {
+                TORCH_CHECK(bias->is_cuda() && bias->is_contiguous() && bias->numel() == sn &&
+                                bias->scalar_type() == a.scalar_type(),
+                            "bias must be a contiguous CUDA tensor of size_n elements in a's dtype");
+                epi.bias = bias->data_ptr();
+            }
+            if (residual.has_value()) {
+                TORCH_CHECK(residual->is_cuda() && residual->is_contiguous() &&
+                                residual->numel() == sm * sn && residual->scalar_type() == a.scalar_type(),
+                            "residual must be a contiguous CUDA [size_m, size_n] tensor in a's dtype");
+                epi.residual = residual->data_ptr();
+            }
+            PetitSolutionHints hints;
+            hints.a_type = a_type;
+            hints.b_type = mx ? PETIT_DTYPE_MXFP4_E2M1 : PETIT_DTYPE_FP4_E2M1;
+            hints.c_type = a_type;
+            hints.require_high_precision = 0;
+            auto fn = mx ? petit_gemm_mxfp4_a16_ex : petit_gemm_nvfp4_a16_ex;
+            int err = fn(c.data_ptr(), a.data_ptr(), b.data_ptr(), s.data_ptr(), gs.data_ptr<float>(),
+                         sm, sn, sk, &hints, static_cast<uint64_t>(sol), &epi, nullptr, stream_of(a));
+            check_status(err, sm, sn, sk, sol);
+            return c;
+        },
+        py::arg("out"), py::arg("a"), py::arg("b"), py::arg("s"), py::arg("global_scale"),
+        py::arg("size_m"), py::arg("size_n"), py::arg("size_k"), py::arg("solution_id") = -1,
+        py::arg("mx") = false, py::arg("bias") = py::none(), py::arg("residual") = py::none());
+
     // extras: row-parallel GEMM fused with the all-reduce of its output (petit_tp.FusedAllReduce)
     m.def(
         "mul_fp4_a16_allreduce_out",

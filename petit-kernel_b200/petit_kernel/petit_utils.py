@@ -88,32 +88,45 @@ def prepare_mxfp4_layer_for_petit(layer: torch.nn.Module) -> None:
     _tag(layer, "MXFP4", part_size_n, part_size_k)
 
 
-def _apply(mul, input, weight, weight_scale, weight_scale_2, size_n, size_k, bias):
+def _apply(mul, input, weight, weight_scale, weight_scale_2, size_n, size_k, bias,
+           residual=None):
     reshaped_x = input.reshape(-1, input.shape[-1])
     out_shape = input.shape[:-1] + (size_n,)
     # solution_id=-1: the library's chooser, which honours the tuned-solution table
     # (petit_kernel.tuning) -- the frameworks' "TODO: use auto-tuning" lives there
-    output = mul(reshaped_x, weight, weight_scale, weight_scale_2, reshaped_x.size(0), size_n,
-                 size_k, -1)
-    if bias is not None:
-        output.add_(bias)  # in place, as the frameworks do
+    if bias is None and residual is None:
+        output = mul(reshaped_x, weight, weight_scale, weight_scale_2, reshaped_x.size(0), size_n,
+                     size_k, -1)
+    else:
+        # fused epilogue: what the frameworks do as `output.add_(bias)` (and the residual add)
+        # right after the op happens on the fp32 accumulator, before the one rounding
+        if bias is not None:
+            bias = bias.to(reshaped_x.dtype).contiguous()
+        if residual is not None:
+            residual = residual.reshape(-1, size_n).contiguous()
+        output = ops.mul_fp4_a16_ex_out(None, reshaped_x, weight, weight_scale, weight_scale_2,
+                                        reshaped_x.size(0), size_n, size_k, -1,
+                                        mul is ops.mul_mxfp4_a16, bias, residual)
     return output.reshape(out_shape)
 
 
 def apply_petit_nvfp4_linear(input: torch.Tensor, weight: torch.Tensor, weight_scale: torch.Tensor,
                              weight_scale_2: torch.Tensor, size_n: int, size_k: int,
-                             bias: torch.Tensor | None = None) -> torch.Tensor:
+                             bias: torch.Tensor | None = None,
+                             residual: torch.Tensor | None = None) -> torch.Tensor:
     """Forward of an NVFP4 linear layer; ``weight_scale_2`` is the float32 device tensor with
-    the global scale (read inside the kernel: no host sync, CUDA-graph safe)."""
+    the global scale (read inside the kernel: no host sync, CUDA-graph safe).  ``bias`` and the
+    optional ``residual`` (same shape as the output) are added inside the GEMM epilogue."""
     return _apply(ops.mul_nvfp4_a16, input, weight, weight_scale, weight_scale_2, size_n, size_k,
-                  bias)
+                  bias, residual)
 
 
 def apply_petit_mxfp4_linear(input: torch.Tensor, weight: torch.Tensor, weight_scale: torch.Tensor,
                              weight_scale_2: torch.Tensor, size_n: int, size_k: int,
-                             bias: torch.Tensor | None = None) -> torch.Tensor:
+                             bias: torch.Tensor | None = None,
+                             residual: torch.Tensor | None = None) -> torch.Tensor:
     return _apply(ops.mul_mxfp4_a16, input, weight, weight_scale, weight_scale_2, size_n, size_k,
-                  bias)
+                  bias, residual)
 
 
 # ---- versioned packed state -----------------------------------------------------

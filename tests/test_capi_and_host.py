@@ -304,8 +304,9 @@ def test_petit_utils_support_checks_and_state_validation():
     with pytest.raises(ValueError, match="not been prepared"):
         pu.export_packed_state(torch.nn.Module())
     # the helpers keep the frameworks' signatures
+    # (plus the optional trailing `residual` of the fused epilogue)
     assert list(inspect.signature(pu.apply_petit_nvfp4_linear).parameters) == [
-        "input", "weight", "weight_scale", "weight_scale_2", "size_n", "size_k", "bias"]
+        "input", "weight", "weight_scale", "weight_scale_2", "size_n", "size_k", "bias", "residual"]
     assert list(inspect.signature(pu.prepare_nvfp4_layer_for_petit).parameters) == ["layer"]
 
 

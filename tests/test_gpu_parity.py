@@ -497,6 +497,55 @@ def test_native_selftest_binary(pk):
     assert r.returncode == 0, r.stdout[-2000:]
 
 
+@pytest.mark.parametrize("fmt,dtype", [("nvfp4", torch.bfloat16), ("nvfp4", torch.float16),
+                                       ("mxfp4", torch.bfloat16)])
+@pytest.mark.parametrize("m,n,k", [(16, 2048, 4096), (5, 1040, 768), (300, 512, 1024)])
+def test_fused_bias_and_residual_epilogue(pk, fmt, dtype, m, n, k):
+    """petit_gemm_*_ex: C = round(acc * gs + bias[n] + residual[m, n]) with the additions in
+    fp32 before the one rounding -- split (stream-K) tiles, a partial n-tile, every token-tile
+    width; checked against the oracle's fp32 reference plus the same terms, and against the
+    unfused op + torch adds (which round twice, hence only close)."""
+    if fmt == "nvfp4":
+        a, q, s, gs = orc.make_nvfp4_case(m, n, k, 7, dtype=dtype)
+        b, sp = pack_nvfp4(pk, q, s, n, k)
+        w = orc.dequant_nvfp4(q.numpy(), s.view(torch.uint8).numpy())
+    else:
+        n = (n + 31) // 32 * 32  # MXFP4 scales come in [N/32, K] (fp4.cc:146-148)
+        a, q, s, gs = orc.make_mxfp4_case(m, n, k, 7)
+        b, sp = pack_mxfp4(pk, q, s, n, k)
+        w = orc.dequant_mxfp4(q.numpy(), s.numpy())
+    g = torch.Generator().manual_seed(3)
+    ref32 = (a.float() @ torch.from_numpy(w).t()) * gs.item()
+    scale = ref32.abs().max().item()
+    bias = (torch.randn(n, generator=g) * scale * 0.1).to(dtype)
+    resid = (torch.randn(m, n, generator=g) * scale * 0.1).to(dtype)
+    ac, gsc = a.cuda(), gs.cuda()
+    mx = fmt == "mxfp4"
+    for bb, rr in ((bias, None), (None, resid), (bias, resid)):
+        want = ref32.clone()
+        if bb is not None:
+            want += bb.float()
+        if rr is not None:
+            want += rr.float()
+        got = pk.ops.mul_fp4_a16_ex_out(None, ac, b, sp, gsc, m, n, k, -1, mx,
+                                        None if bb is None else bb.cuda(),
+                                        None if rr is None else rr.cuda())
+        assert got.dtype == dtype and orc.max_rel_err(got, want) <= GEMM_TOL
+    # residual may alias the output (in-place residual stream update)
+    out = resid.cuda().clone()
+    pk.ops.mul_fp4_a16_ex_out(out, ac, b, sp, gsc, m, n, k, -1, mx, bias.cuda(), out)
+    assert orc.max_rel_err(out, ref32 + bias.float() + resid.float()) <= GEMM_TOL
+    # the glue uses it instead of output.add_(bias)
+    from petit_kernel import petit_utils as pu
+
+    apply = pu.apply_petit_mxfp4_linear if mx else pu.apply_petit_nvfp4_linear
+    y = apply(ac.view(1, m, k), b, sp, gsc, n, k, bias.cuda(), resid.cuda().view(1, m, n))
+    assert tuple(y.shape) == (1, m, n)
+    assert orc.max_rel_err(y.view(m, n), ref32 + bias.float() + resid.float()) <= GEMM_TOL
+    with pytest.raises(RuntimeError):
+        pk.ops.mul_fp4_a16_ex_out(None, ac, b, sp, gsc, m, n, k, -1, mx, bias.cuda()[:-1].contiguous(), None)
+
+
 def test_cpp_source_compat_header_runs_a_gemm(pk, tmp_path):
     """The reference-style C++ unit (tests/native/compat_user.cc over gemm_compat.h) repacks and
     multiplies on the GPU through the namespace-compatible shim and the hal::Device object."""

@@ -247,10 +247,18 @@ int petit_gemm_mxfp4_a16_allreduce(void *c, const void *a, const void *b, const 
  * happens on the fp32 accumulator before the single rounding to the output type:
  *     C[m, n] = round(acc[m, n] * global_scale + bias[n] + residual[m, n])
  * bias: [n], residual: [m, n] row-major, both in the output type, either may be NULL;
- * residual may alias c.  activation must be PETIT_ACT_NONE (reserved).  `ar` may be NULL (plain
- * GEMM) or a fused all-reduce context; then bias / residual are added to THIS rank's partial,
- * i.e. a row-parallel layer passes them on one rank only. */
+ * residual may alias c.  `ar` may be NULL (plain GEMM) or a fused all-reduce context; then bias /
+ * residual are added to THIS rank's partial, i.e. a row-parallel layer passes them on one rank
+ * only.
+ * activation = PETIT_ACT_SILU_MUL fuses the MLP's act-and-mul into the gate_up projection:
+ *     C[m, i] = round(round(silu(G[m, i])) * U[m, i]),  G / U the rounded GEMM outputs,
+ * the arithmetic of the unfused path (GEMM, then silu_and_mul), so the same bits.  C is
+ * [m, n / 2].  The weight rows must have been interleaved per 128-row tile BEFORE repacking:
+ * rows [128 t, 128 t + 64) = gate rows [64 t, 64 t + 64), rows [128 t + 64, 128 t + 128) = up
+ * rows [64 t, 64 t + 64) (petit_kernel.petit_utils.interleave_gate_up does it; bias, if any, is
+ * indexed in that row order).  Needs n % 128 == 0, no residual, no all-reduce. */
 #define PETIT_ACT_NONE 0
+#define PETIT_ACT_SILU_MUL 1
 typedef struct PetitEpilogue {
     const void *bias;
     const void *residual;

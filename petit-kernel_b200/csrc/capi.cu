@@ -347,13 +347,22 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
     args.trace = g_trace;
     args.bias = nullptr;
     args.residual = nullptr;
+    args.act_silu_mul = 0;
     if (epi) {
-        if (epi->activation != PETIT_ACT_NONE) return PETIT_ERROR_KERNEL_SHAPE;
+        if (epi->activation != PETIT_ACT_NONE && epi->activation != PETIT_ACT_SILU_MUL)
+            return PETIT_ERROR_KERNEL_SHAPE;
+        if (epi->activation == PETIT_ACT_SILU_MUL) {
+            // gate / up rows interleaved per 128-row tile; no residual ([m, n] vs [m, n / 2]) and no
+            // all-reduce (gate_up is column parallel); m in 16-token groups of up to 256 tokens
+            if (n % layout::kTileN != 0 || epi->residual || ar) return PETIT_ERROR_PROBLEM_SHAPE;
+            if (((n / 2) * 2) % 16 != 0) return PETIT_ERROR_PROBLEM_SHAPE;
+        }
         // 2-byte elements, read with scalar loads: natural alignment is enough
         if (((reinterpret_cast<uintptr_t>(epi->bias) | reinterpret_cast<uintptr_t>(epi->residual)) & 1) != 0)
             return PETIT_ERROR_PROBLEM_SHAPE;
         args.bias = epi->bias;
         args.residual = epi->residual;
+        args.act_silu_mul = epi->activation == PETIT_ACT_SILU_MUL ? 1u : 0u;
     }
     args.ar_world = 0;
     args.ar_rank = 0;

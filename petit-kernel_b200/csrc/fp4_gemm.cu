@@ -618,28 +618,45 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 // the previous occupant of this TMEM A stage must have been consumed
                 mbar_wait_addr(ab, aph);
                 tc_fence_after();
+                // MXFP4 scales >= 2^-1 (e8m0 > 125) need a second exact multiply.  Real MX
+                // weight scales are far below that, so the decision is taken once per stage for
+                // the whole warp and the common case runs a loop body without the second
+                // multiply (it used to be issued unconditionally: 64 of 366 instructions).
+                bool any_two = false;
+                if (C::kIsMx) {
+                    bool mine = false;
 #pragma unroll
-                for (int ci = 0; ci < kMyChunks; ++ci) {
-                    const uint32_t bits = scw[ci / 2] >> ((ci & 1) * 8 * kScBytesPerChunk);
-                    bool two_step = false;
-                    if (C::kIsMx) two_step = __any_sync(0xffffffffu, mx_needs_two_step(bits));
-                    const uint32_t mult = chunk_multiplier<MODE>(bits, two_step);
-                    uint32_t out[16];
+                    for (int p = 0; p < kScLoads; ++p)
+                        mine = mine || mx_needs_two_step(scw[p]) || mx_needs_two_step(scw[p] >> 8);
+                    any_two = __any_sync(0xffffffffu, mine);
+                }
+                auto convert = [&](auto two_tag) {
+                    constexpr bool kTwo = decltype(two_tag)::value;
+#pragma unroll
+                    for (int ci = 0; ci < kMyChunks; ++ci) {
+                        const uint32_t bits = scw[ci / 2] >> ((ci & 1) * 8 * kScBytesPerChunk);
+                        const uint32_t mult = chunk_multiplier<MODE>(bits, kTwo);
+                        uint32_t out[16];
 #if PETIT_KO & 2
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) out[j] = q[ci].x + j;
+                        for (int j = 0; j < 16; ++j) out[j] = q[ci].x + j;
 #else
-                    dequant_chunk<MODE>(q[ci], mult, two_step, out);
+                        dequant_chunk<MODE>(q[ci], mult, kTwo, out);
 #endif
 #if PETIT_KO & 16
-                    asm volatile("" ::"r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3]), "r"(out[4]),
-                                 "r"(out[5]), "r"(out[6]), "r"(out[7]), "r"(out[8]), "r"(out[9]),
-                                 "r"(out[10]), "r"(out[11]), "r"(out[12]), "r"(out[13]),
-                                 "r"(out[14]), "r"(out[15]));
+                        asm volatile("" ::"r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3]), "r"(out[4]),
+                                     "r"(out[5]), "r"(out[6]), "r"(out[7]), "r"(out[8]), "r"(out[9]),
+                                     "r"(out[10]), "r"(out[11]), "r"(out[12]), "r"(out[13]),
+                                     "r"(out[14]), "r"(out[15]));
 #else
-                    tmem_st_x16(tm + ci * 16, out);
+                        tmem_st_x16(tm + ci * 16, out);
 #endif
-                }
+                    }
+                };
+                if (C::kIsMx && any_two)
+                    convert(std::true_type{});
+                else
+                    convert(std::false_type{});
                 if (!(PETIT_KO & 32)) tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
@@ -1133,6 +1150,50 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                         bulk_commit_group();
                     }
                     out_buf = out_buf == C::kOutBufs - 1 ? 0 : out_buf + 1;
+                } else if (args.act_silu_mul) {
+                    // ---- fused SiLU(gate) * up (the MLP's gate_up projection; rows of every
+                    // 128-row tile were interleaved at weight-load time: 0-63 gate, 64-127 the
+                    // matching up rows).  Same arithmetic as the unfused path the frameworks run
+                    // (GEMM output rounded to 16 bit, silu in fp32 rounded to 16 bit, product
+                    // rounded to 16 bit), so the result is the same bits; output tile is
+                    // [16 tokens][64 columns] of c[m, n / 2].
+                    uint16_t *stg = reinterpret_cast<uint16_t *>(team_stage + out_buf * C::kOutStageBytes);
+                    if (ew_tid == 0) bulk_wait_group_read<C::kOutBufs - 2>();
+                    named_bar_sync(team_bar, kNumEpilogueWarps * 32); // buffer drained
+                    if (row >= 64) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) stg[j * 64 + (row - 64)] = to_bits16<C::kIsBf16>(v[j]);
+                    }
+                    named_bar_sync(team_bar, kNumEpilogueWarps * 32); // up rows visible
+                    uint16_t r16[16];
+                    if (row < 64) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const uint16_t ub = stg[j * 64 + row];
+                            const uint16_t gb = to_bits16<C::kIsBf16>(v[j]);
+                            const float gf = C::kIsBf16 ? __uint_as_float((uint32_t)gb << 16)
+                                                        : __half2float(__ushort_as_half(gb));
+                            const float uf = C::kIsBf16 ? __uint_as_float((uint32_t)ub << 16)
+                                                        : __half2float(__ushort_as_half(ub));
+                            const uint16_t sb = to_bits16<C::kIsBf16>(gf / (1.0f + expf(-gf)));
+                            const float sf = C::kIsBf16 ? __uint_as_float((uint32_t)sb << 16)
+                                                        : __half2float(__ushort_as_half(sb));
+                            r16[j] = to_bits16<C::kIsBf16>(sf * uf);
+                        }
+                    }
+                    named_bar_sync(team_bar, kNumEpilogueWarps * 32); // up rows consumed
+                    if (row < 64) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) stg[j * 64 + row] = r16[j];
+                    }
+                    fence_proxy_async();
+                    named_bar_sync(team_bar, kNumEpilogueWarps * 32);
+                    if (ew_tid == 0) {
+                        // tmap_out describes c[m, n / 2] with [16][64] boxes in this mode
+                        tma_store_2d(&tmap_out, stg, (int)(g.n_tile * 64), (int)(m0 + c0));
+                        bulk_commit_group();
+                    }
+                    out_buf = out_buf == C::kOutBufs - 1 ? 0 : out_buf + 1;
                 } else if (!PETIT_DBG(args.debug_flags, 64u)) {
                     // [16 tokens][128 rows] 16-bit staging tile -> one TMA store; the tensor
                     // map clips tokens >= M and rows >= N.  Three buffers in rotation: the
@@ -1237,9 +1298,11 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return kLaunchCudaError;
     // output [M, N] 16-bit row-major; the epilogue stores [16 tokens][128 rows] boxes
     CUtensorMap tmap_out;
-    const cuuint64_t odims[2] = {args.n, args.m};
-    const cuuint64_t ostrides[1] = {(cuuint64_t)args.n * 2};
-    const cuuint32_t obox[2] = {kTileN, 16};
+    // (fused SiLU * mul: c is [M, N / 2] and a tile stores a [16 tokens][64 columns] box)
+    const cuuint64_t out_n = args.act_silu_mul ? args.n / 2 : args.n;
+    const cuuint64_t odims[2] = {out_n, args.m};
+    const cuuint64_t ostrides[1] = {out_n * 2};
+    const cuuint32_t obox[2] = {args.act_silu_mul ? 64u : kTileN, 16};
     r = encode(&tmap_out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, args.c, odims, ostrides, obox, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

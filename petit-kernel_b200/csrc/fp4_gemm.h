@@ -21,6 +21,8 @@ struct GemmArgs {
     void *c;                // [m, n] 16-bit row-major
     const void *bias;       // optional [n] in the output type: added in fp32 before rounding
     const void *residual;   // optional [m, n] in the output type: added in fp32 before rounding
+    uint32_t act_silu_mul;  // 1: rows 0-63 of every n-tile are gate rows, 64-127 the matching up
+                            // rows; c is [m, n / 2] = silu(gate) * up
     float *ws_partials;     // stream-K partial tiles
     unsigned *ws_counters;  // per-tile arrival counters (zero between launches)
     unsigned *ws_status;    // sticky: != 0 once a split-tile reducer gave up waiting (watchdog)

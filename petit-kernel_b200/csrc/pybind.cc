@@ -396,12 +396,13 @@ PYBIND11_MODULE(ops, m) {
         [](const c10::optional<torch::Tensor> &out, const torch::Tensor &a, const torch::Tensor &b,
            const torch::Tensor &s, const torch::Tensor &gs, int64_t sm, int64_t sn, int64_t sk,
            int64_t sol, bool mx, const c10::optional<torch::Tensor> &bias,
-           const c10::optional<torch::Tensor> &residual) {
+           const c10::optional<torch::Tensor> &residual, bool silu_mul) {
             PetitDataType a_type = dtype_of(a);
             check_gemm_operands(a, b, s, gs, sm, sn, sk, sn * sk / (mx ? 32 : 16));
             c10::cuda::CUDAGuard guard(a.device());
-            torch::Tensor c = alloc_or_check_out(out, a, sm, sn);
-            PetitEpilogue epi = {nullptr, nullptr, PETIT_ACT_NONE, 0};
+            TORCH_CHECK(!silu_mul || sn % 128 == 0, "silu_mul needs size_n % 128 == 0");
+            torch::Tensor c = alloc_or_check_out(out, a, sm, silu_mul ? sn / 2 : sn);
+            PetitEpilogue epi = {nullptr, nullptr, silu_mul ? PETIT_ACT_SILU_MUL : PETIT_ACT_NONE, 0};
             if (bias.has_value()) {
                 TORCH_CHECK(bias->is_cuda() && bias->is_contiguous() && bias->numel() == sn &&
                                 bias->scalar_type() == a.scalar_type(),
@@ -427,7 +428,8 @@ PYBIND11_MODULE(ops, m) {
         },
         py::arg("out"), py::arg("a"), py::arg("b"), py::arg("s"), py::arg("global_scale"),
         py::arg("size_m"), py::arg("size_n"), py::arg("size_k"), py::arg("solution_id") = -1,
-        py::arg("mx") = false, py::arg("bias") = py::none(), py::arg("residual") = py::none());
+        py::arg("mx") = false, py::arg("bias") = py::none(), py::arg("residual") = py::none(),
+        py::arg("silu_mul") = false);
 
     // extras: row-parallel GEMM fused with the all-reduce of its output (petit_tp.FusedAllReduce)
     m.def(

@@ -60,12 +60,34 @@ def _tag(layer: torch.nn.Module, fmt: str, size_n: int, size_k: int) -> None:
     layer.petit_size_n, layer.petit_size_k = int(size_n), int(size_k)
 
 
-def prepare_nvfp4_layer_for_petit(layer: torch.nn.Module) -> None:
+def interleave_gate_up(t: torch.Tensor) -> torch.Tensor:
+    """Row order the fused SiLU * mul epilogue needs (petit.h, PETIT_ACT_SILU_MUL): ``t`` is a
+    merged gate_up tensor ``[2 I, ...]`` = gate rows then up rows (weights, block scales or a
+    bias); the result holds, per 128 rows, 64 gate rows followed by the 64 matching up rows."""
+    two_i = t.shape[0]
+    assert two_i % 128 == 0, "gate_up rows must be a multiple of 128"
+    i = two_i // 2
+    gate = t[:i].reshape(i // 64, 64, *t.shape[1:])
+    up = t[i:].reshape(i // 64, 64, *t.shape[1:])
+    return torch.cat((gate, up), dim=1).reshape(t.shape).contiguous()
+
+
+def prepare_nvfp4_layer_for_petit(layer: torch.nn.Module, fuse_silu_mul: bool = False) -> None:
     """``process_weights_after_loading`` of an NVFP4 linear layer: ``layer.weight`` is the
     checkpoint's packed e2m1 bytes ``[N, K/2]`` (any 1-byte dtype) of the local shard,
-    ``layer.weight_scale`` its ``float8_e4m3fn [N, K/16]`` block scales."""
+    ``layer.weight_scale`` its ``float8_e4m3fn [N, K/16]`` block scales.
+    ``fuse_silu_mul=True`` (a merged gate_up projection): interleaves gate and up rows so that
+    ``apply_petit_nvfp4_linear(..., silu_mul=True)`` returns ``silu(gate) * up`` directly."""
     part_size_n = layer.output_size_per_partition
     part_size_k = layer.input_size_per_partition
+    if fuse_silu_mul:
+        layer.weight = torch.nn.Parameter(interleave_gate_up(layer.weight.data), requires_grad=False)
+        layer.weight_scale = torch.nn.Parameter(
+            interleave_gate_up(layer.weight_scale.data.view(torch.uint8)).view(layer.weight_scale.dtype),
+            requires_grad=False)
+        if getattr(layer, "bias", None) is not None:
+            layer.bias = torch.nn.Parameter(interleave_gate_up(layer.bias.data), requires_grad=False)
+        layer.petit_silu_mul = True
     qweight = layer.weight.view(torch.int32).contiguous()
     petit_qweight = ops.repack_nvfp4(qweight, part_size_n, part_size_k)
     layer.weight = torch.nn.Parameter(petit_qweight, requires_grad=False)
@@ -89,12 +111,18 @@ def prepare_mxfp4_layer_for_petit(layer: torch.nn.Module) -> None:
 
 
 def _apply(mul, input, weight, weight_scale, weight_scale_2, size_n, size_k, bias,
-           residual=None):
+           residual=None, silu_mul=False):
     reshaped_x = input.reshape(-1, input.shape[-1])
-    out_shape = input.shape[:-1] + (size_n,)
+    out_shape = input.shape[:-1] + (size_n // 2 if silu_mul else size_n,)
     # solution_id=-1: the library's chooser, which honours the tuned-solution table
     # (petit_kernel.tuning) -- the frameworks' "TODO: use auto-tuning" lives there
-    if bias is None and residual is None:
+    if silu_mul:
+        if bias is not None:
+            bias = bias.to(reshaped_x.dtype).contiguous()
+        output = ops.mul_fp4_a16_ex_out(None, reshaped_x, weight, weight_scale, weight_scale_2,
+                                        reshaped_x.size(0), size_n, size_k, -1,
+                                        mul is ops.mul_mxfp4_a16, bias, None, True)
+    elif bias is None and residual is None:
         output = mul(reshaped_x, weight, weight_scale, weight_scale_2, reshaped_x.size(0), size_n,
                      size_k, -1)
     else:
@@ -113,20 +141,24 @@ def _apply(mul, input, weight, weight_scale, weight_scale_2, size_n, size_k, bia
 def apply_petit_nvfp4_linear(input: torch.Tensor, weight: torch.Tensor, weight_scale: torch.Tensor,
                              weight_scale_2: torch.Tensor, size_n: int, size_k: int,
                              bias: torch.Tensor | None = None,
-                             residual: torch.Tensor | None = None) -> torch.Tensor:
+                             residual: torch.Tensor | None = None,
+                             silu_mul: bool = False) -> torch.Tensor:
     """Forward of an NVFP4 linear layer; ``weight_scale_2`` is the float32 device tensor with
     the global scale (read inside the kernel: no host sync, CUDA-graph safe).  ``bias`` and the
-    optional ``residual`` (same shape as the output) are added inside the GEMM epilogue."""
+    optional ``residual`` (same shape as the output) are added inside the GEMM epilogue;
+    ``silu_mul=True`` (layer prepared with ``fuse_silu_mul=True``) returns
+    ``silu(gate) * up`` of shape ``[..., size_n / 2]``."""
     return _apply(ops.mul_nvfp4_a16, input, weight, weight_scale, weight_scale_2, size_n, size_k,
-                  bias, residual)
+                  bias, residual, silu_mul)
 
 
 def apply_petit_mxfp4_linear(input: torch.Tensor, weight: torch.Tensor, weight_scale: torch.Tensor,
                              weight_scale_2: torch.Tensor, size_n: int, size_k: int,
                              bias: torch.Tensor | None = None,
-                             residual: torch.Tensor | None = None) -> torch.Tensor:
+                             residual: torch.Tensor | None = None,
+                             silu_mul: bool = False) -> torch.Tensor:
     return _apply(ops.mul_mxfp4_a16, input, weight, weight_scale, weight_scale_2, size_n, size_k,
-                  bias, residual)
+                  bias, residual, silu_mul)
 
 
 # ---- versioned packed state -----------------------------------------------------

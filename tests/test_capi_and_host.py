@@ -306,8 +306,14 @@ def test_petit_utils_support_checks_and_state_validation():
     # the helpers keep the frameworks' signatures
     # (plus the optional trailing `residual` of the fused epilogue)
     assert list(inspect.signature(pu.apply_petit_nvfp4_linear).parameters) == [
-        "input", "weight", "weight_scale", "weight_scale_2", "size_n", "size_k", "bias", "residual"]
-    assert list(inspect.signature(pu.prepare_nvfp4_layer_for_petit).parameters) == ["layer"]
+        "input", "weight", "weight_scale", "weight_scale_2", "size_n", "size_k", "bias", "residual",
+        "silu_mul"]
+    # gate / up interleave of the fused SiLU * mul epilogue: per 128 rows 64 gate + 64 up rows
+    t = torch.arange(256).view(256, 1)
+    il = pu.interleave_gate_up(t).view(-1)
+    assert il[:64].tolist() == list(range(64)) and il[64:128].tolist() == list(range(128, 192))
+    assert il[128:192].tolist() == list(range(64, 128)) and il[192:].tolist() == list(range(192, 256))
+    assert list(inspect.signature(pu.prepare_nvfp4_layer_for_petit).parameters) == ["layer", "fuse_silu_mul"]
 
 
 def test_tuning_table_round_trip_through_python(tmp_path):

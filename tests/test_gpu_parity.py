@@ -546,6 +546,41 @@ def test_fused_bias_and_residual_epilogue(pk, fmt, dtype, m, n, k):
         pk.ops.mul_fp4_a16_ex_out(None, ac, b, sp, gsc, m, n, k, -1, mx, bias.cuda()[:-1].contiguous(), None)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,inter,k", [(16, 1024, 2048), (3, 128, 512), (200, 512, 1024)])
+def test_fused_silu_mul_epilogue(pk, dtype, m, inter, k):
+    """PETIT_ACT_SILU_MUL: the gate_up projection returns silu(gate) * up.  Reference = what the
+    frameworks run unfused on the same kernel's output: GEMM (rounded), silu in fp32 (rounded),
+    product (rounded).  Same arithmetic, so equal up to the last bit of expf."""
+    from petit_kernel import petit_utils as pu
+
+    n = 2 * inter
+    a, q, s, gs = orc.make_nvfp4_case(m, n, k, 17, dtype=dtype)
+    ac, gsc = a.cuda(), (gs * 0.02).cuda()  # keep silu's argument in its interesting range
+    b, sp = pack_nvfp4(pk, q, s, n, k)
+    c = pk.mul_nvfp4_a16(ac, b, sp, gsc, m, n, k, -1)          # unfused: [m, 2 I] = gate | up
+    want = (torch.nn.functional.silu(c[:, :inter].float()).to(dtype).float() * c[:, inter:].float()).to(dtype)
+    lay = _FakeLinear(q, s, n, k)
+    pu.prepare_nvfp4_layer_for_petit(lay, fuse_silu_mul=True)
+    got = pu.apply_petit_nvfp4_linear(ac, lay.weight, lay.weight_scale, gsc, n, k, None, None, True)
+    assert tuple(got.shape) == (m, inter) and got.dtype == dtype
+    diff = (got.float() - want.float()).abs()
+    tol = want.float().abs() * 2 ** -6 + 1e-6   # one 16-bit ulp: expf vs torch's exp
+    assert bool((diff <= tol).all()), diff.max().item()
+    assert (got == want).float().mean().item() > 0.98
+    # with a bias (indexed in the interleaved row order)
+    g = torch.Generator().manual_seed(5)
+    bias = (torch.randn(n, generator=g) * 0.5).to(dtype)
+    cb = (c.float() + bias.cuda().float()).to(dtype)  # unfused rounds the GEMM first: close, not equal
+    want_b = (torch.nn.functional.silu(cb[:, :inter].float()) * cb[:, inter:].float())
+    got_b = pu.apply_petit_nvfp4_linear(ac, lay.weight, lay.weight_scale, gsc, n, k,
+                                        pu.interleave_gate_up(bias).cuda(), None, True)
+    assert orc.max_rel_err(got_b.cpu(), want_b.cpu()) <= 2e-2
+    with pytest.raises(RuntimeError):  # residual has the GEMM's shape, the output does not
+        pk.ops.mul_fp4_a16_ex_out(None, ac, lay.weight, lay.weight_scale, gsc, m, n, k, -1, False,
+                                  None, c, True)
+
+
 def test_cpp_source_compat_header_runs_a_gemm(pk, tmp_path):
     """The reference-style C++ unit (tests/native/compat_user.cc over gemm_compat.h) repacks and
     multiplies on the GPU through the namespace-compatible shim and the hal::Device object."""

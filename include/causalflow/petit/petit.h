@@ -263,8 +263,25 @@ typedef struct PetitEpilogue {
     const void *bias;
     const void *residual;
     int32_t activation;
-    int32_t reserved;
+    int32_t weight_layout; /* PETIT_WEIGHT_LAYOUT_*: how b was repacked (below) */
 } PetitEpilogue;
+
+/* Packed weight layouts.  petit_repack_fp4_weights produces the DEFAULT layout, whose in-word
+ * bit order is native to bf16 (one shift + one LOP3 per pair of weights) and which every
+ * activation type can use.  For fp16 activations the F16_NATIVE variant -- same tiles, words in
+ * the native nibble order -- lets the kernel convert a pair with a single cvt.rn.f16x2.e2m1x2
+ * (2 instead of ~5 instructions per pair: fp16 decode is then HBM-bound).  It is only valid
+ * with NVFP4 weights and fp16 activations, and must be named in PetitEpilogue.weight_layout of
+ * the petit_gemm_nvfp4_a16_ex call (the Python ops carry it in the packed tensor's shape). */
+#define PETIT_WEIGHT_LAYOUT_DEFAULT 0
+#define PETIT_WEIGHT_LAYOUT_F16_NATIVE 1
+int petit_repack_fp4_weights_layout(uint32_t *out, const uint32_t *in, unsigned in_chan,
+                                    unsigned out_chan, int weight_layout, petit_stream_t stream);
+int petit_unpack_fp4_weights_layout(uint32_t *out, const uint32_t *in_packed, unsigned in_chan,
+                                    unsigned out_chan, int weight_layout, petit_stream_t stream);
+int petit_dequant_packed_nvfp4_layout(void *out, const void *w_packed, const void *scales_packed,
+                                      float global_scale, int out_type, unsigned k, unsigned n,
+                                      int weight_layout, petit_stream_t stream);
 int petit_gemm_nvfp4_a16_ex(void *c, const void *a, const void *b, const void *scales,
                             const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
                             const PetitSolutionHints *hints, uint64_t solution_id,
@@ -275,6 +292,26 @@ int petit_gemm_mxfp4_a16_ex(void *c, const void *a, const void *b, const void *s
                             const PetitSolutionHints *hints, uint64_t solution_id,
                             const PetitEpilogue *epilogue, const PetitFusedAllReduce *ar,
                             petit_stream_t stream);
+
+/* Grouped (MoE) GEMM (the reference has no grouped entry point): one
+ * call for `num_groups` independent problems C_g[m_g, n] = A_g[m_g, k] x dequant(B_g)^T x gs_g
+ * with a common n, k and type -- the token-grouped expert GEMMs of an MoE layer (tokens sorted
+ * by expert, m_g = tokens routed to expert g, groups with m_g == 0 are skipped).  This version
+ * issues the groups back to back on the stream (each is the stream-K kernel, chained by
+ * programmatic dependent launch so the next expert's weights stream while the previous one
+ * drains); it returns the first non-zero status and stops.  A single-launch grouped scheduler
+ * is future work. */
+typedef struct PetitGroupedProblem {
+    void *c;
+    const void *a;
+    const void *b;
+    const void *scales;
+    const float *global_scale_dev;
+    unsigned m;
+} PetitGroupedProblem;
+int petit_gemm_fp4_a16_grouped(const PetitGroupedProblem *problems, unsigned num_groups, unsigned n,
+                               unsigned k, const PetitSolutionHints *hints, uint64_t solution_id,
+                               const PetitEpilogue *epilogue, petit_stream_t stream);
 
 size_t petit_fused_allreduce_recv_bytes(unsigned n);
 size_t petit_fused_allreduce_state_bytes(void);

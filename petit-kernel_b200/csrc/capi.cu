@@ -409,9 +409,15 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
         }();
         args.skew_cycles = (uint32_t)skew;
     }
-    const int mode = d.elem_b == kElemMx
-                         ? gemm::kModeMxBf16
-                         : (d.mfma == kMfmaBf16 ? gemm::kModeNvBf16 : gemm::kModeNvF16);
+    int mode = d.elem_b == kElemMx
+                   ? gemm::kModeMxBf16
+                   : (d.mfma == kMfmaBf16 ? gemm::kModeNvBf16 : gemm::kModeNvF16);
+    if (epi && epi->weight_layout != PETIT_WEIGHT_LAYOUT_DEFAULT) {
+        // the fp16-native layout only fits NVFP4 weights multiplied with fp16 activations
+        if (epi->weight_layout != PETIT_WEIGHT_LAYOUT_F16_NATIVE || mode != gemm::kModeNvF16)
+            return PETIT_ERROR_KERNEL_SHAPE;
+        mode = gemm::kModeNvF16N;
+    }
     switch (gemm::launch(mode, d.ntok, args, num_sms, stream)) {
     case gemm::kLaunchOk: return PETIT_OK;
     case gemm::kLaunchBadShape: return PETIT_ERROR_PROBLEM_SHAPE;
@@ -483,6 +489,24 @@ int petit_gemm_mxfp4_a16_ex(void *c, const void *a, const void *b, const void *s
                             petit_stream_t stream) {
     return gemm_impl(c, a, b, scales, global_scale_dev, m, n, k, hints, solution_id, true,
                      reinterpret_cast<cudaStream_t>(stream), ar, epilogue);
+}
+
+int petit_gemm_fp4_a16_grouped(const PetitGroupedProblem *problems, unsigned num_groups, unsigned n,
+                               unsigned k, const PetitSolutionHints *hints, uint64_t solution_id,
+                               const PetitEpilogue *epilogue, petit_stream_t stream) {
+    if (!problems && num_groups) return PETIT_ERROR_PROBLEM_SHAPE;
+    if (!hints) return PETIT_ERROR_KERNEL_SHAPE;
+    if (epilogue && epilogue->residual) return PETIT_ERROR_PROBLEM_SHAPE; // per-group shapes differ
+    const bool mx = hints->b_type == PETIT_DTYPE_MXFP4_E2M1;
+    for (unsigned g = 0; g < num_groups; ++g) {
+        const PetitGroupedProblem &p = problems[g];
+        if (p.m == 0) continue;
+        const int rc = gemm_impl(p.c, p.a, p.b, p.scales, p.global_scale_dev, p.m, n, k, hints,
+                                 solution_id, mx, reinterpret_cast<cudaStream_t>(stream), nullptr,
+                                 epilogue);
+        if (rc != PETIT_OK) return rc;
+    }
+    return PETIT_OK;
 }
 
 size_t petit_fused_allreduce_recv_bytes(unsigned n) { return gemm::ar_recv_bytes(n); }
@@ -568,6 +592,39 @@ int petit_repack_fp4_weights(uint32_t *out, const uint32_t *in, unsigned in_chan
     note_weight_writer(reinterpret_cast<cudaStream_t>(stream));
     return repack::weights(out, in, in_chan, out_chan, false,
                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int petit_repack_fp4_weights_layout(uint32_t *out, const uint32_t *in, unsigned in_chan,
+                                    unsigned out_chan, int weight_layout, petit_stream_t stream) {
+    if (weight_layout != PETIT_WEIGHT_LAYOUT_DEFAULT && weight_layout != PETIT_WEIGHT_LAYOUT_F16_NATIVE)
+        return PETIT_ERROR_PROBLEM_SHAPE;
+    note_weight_writer(reinterpret_cast<cudaStream_t>(stream));
+    return repack::weights(out, in, in_chan, out_chan, false, reinterpret_cast<cudaStream_t>(stream),
+                           weight_layout == PETIT_WEIGHT_LAYOUT_F16_NATIVE);
+}
+
+int petit_unpack_fp4_weights_layout(uint32_t *out, const uint32_t *in_packed, unsigned in_chan,
+                                    unsigned out_chan, int weight_layout, petit_stream_t stream) {
+    if (weight_layout != PETIT_WEIGHT_LAYOUT_DEFAULT && weight_layout != PETIT_WEIGHT_LAYOUT_F16_NATIVE)
+        return PETIT_ERROR_PROBLEM_SHAPE;
+    return repack::weights(out, in_packed, in_chan, out_chan, true,
+                           reinterpret_cast<cudaStream_t>(stream),
+                           weight_layout == PETIT_WEIGHT_LAYOUT_F16_NATIVE);
+}
+
+int petit_dequant_packed_nvfp4_layout(void *out, const void *w_packed, const void *scales_packed,
+                                      float global_scale, int out_type, unsigned k, unsigned n,
+                                      int weight_layout, petit_stream_t stream) {
+    int mode = dequant_mode(out_type, false);
+    if (mode < 0) return -1;
+    if (weight_layout == PETIT_WEIGHT_LAYOUT_F16_NATIVE) {
+        if (mode != gemm::kModeNvF16) return -1;
+        mode = gemm::kModeNvF16N;
+    } else if (weight_layout != PETIT_WEIGHT_LAYOUT_DEFAULT) {
+        return -1;
+    }
+    return repack::dequant_dense(out, w_packed, scales_packed, global_scale, mode, true, k, n,
+                                 reinterpret_cast<cudaStream_t>(stream));
 }
 
 int petit_unpack_fp4_weights(uint32_t *out, const uint32_t *in_packed, unsigned in_chan,

@@ -20,6 +20,7 @@
 #pragma once
 
 #include "fp4_gemm.h"
+#include "sm100_ptx.cuh"
 
 #include <cstdint>
 #include <cuda_bf16.h>
@@ -30,6 +31,7 @@ namespace petit::dq {
 using petit::gemm::kModeMxBf16;
 using petit::gemm::kModeNvBf16;
 using petit::gemm::kModeNvF16;
+using petit::gemm::kModeNvF16N;
 
 __device__ __forceinline__ uint32_t hmul2_f16(uint32_t a, uint32_t b) {
     uint32_t d;
@@ -88,7 +90,8 @@ __device__ __forceinline__ void extract_f16(uint32_t q, uint32_t (&x)[4]) {
 // Power of two folded out of the A operand and applied in the epilogue: the A
 // operand holds  w * 2^-8 (NVFP4 bf16),  w * 2^-7 (NVFP4 fp16)  or  w * 4 (MXFP4).
 template <int MODE> __host__ __device__ constexpr float epilogue_factor() {
-    return MODE == kModeMxBf16 ? 0.25f : (MODE == kModeNvBf16 ? 256.0f : 128.0f);
+    return MODE == kModeNvF16N ? 1.0f
+                               : (MODE == kModeMxBf16 ? 0.25f : (MODE == kModeNvBf16 ? 256.0f : 128.0f));
 }
 
 __device__ __forceinline__ bool mx_needs_two_step(uint32_t bits) { return (bits & 0xff) > 125; }
@@ -108,6 +111,11 @@ __device__ __forceinline__ uint32_t chunk_multiplier(uint32_t bits, bool two_ste
         return field * 0x00800080u;
     }
     const uint32_t x = __byte_perm(bits, 0, 0x4140);     // bytes (b0, b1) -> 16-bit lanes
+    if (MODE == kModeNvF16N) {
+        // an E5M3 byte IS the top 8 bits (below the sign) of the fp16 with the same value:
+        // exponent field e5, mantissa m -> the exact scale, 0 for a zero byte
+        return x << 7;
+    }
     const uint32_t nz = (x + 0x00ff00ffu) & 0x01000100u; // bit 8 of a lane = (byte != 0)
     if (MODE == kModeNvF16) {
         // fp16(scale * 2^7): exponent field e5 + 7, top 3 mantissa bits = m
@@ -123,6 +131,21 @@ template <int MODE>
 __device__ __forceinline__ void dequant_chunk(const uint4 q, uint32_t mult, bool two_step,
                                               uint32_t (&out)[16]) {
     const uint32_t words[4] = {q.x, q.y, q.z, q.w};
+    if (MODE == kModeNvF16N) {
+        // fp16-native layout: byte b of a word = elements (2b, 2b + 1), low nibble first.
+        // One F2FP (cvt.rn.f16x2.e2m1x2) per pair gives the exact e2m1 values, one HMUL2 by
+        // the exact fp16 scale the exact weight: 2 instructions per pair.
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t x[4];
+            petit::ptx::cvt_e2m1x8_to_f16x2x4(words[w], x[0], x[1], x[2], x[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                out[w * 4 + j] = w < 2 ? hmul2_bcast<false, false>(x[j], mult)
+                                       : hmul2_bcast<false, true>(x[j], mult);
+        }
+        return;
+    }
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
         uint32_t x[4];

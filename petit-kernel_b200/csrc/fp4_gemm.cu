@@ -89,7 +89,7 @@ constexpr int kSmemBudget = 227 * 1024;
 
 template <int MODE, int NTOK, int KS> struct Cfg {
     static constexpr bool kIsMx = MODE == kModeMxBf16;
-    static constexpr bool kIsBf16 = MODE != kModeNvF16;
+    static constexpr bool kIsBf16 = MODE == kModeNvBf16 || MODE == kModeMxBf16;
     static constexpr int kSubs = KS / 64;          // 64-k slabs per stage
     static constexpr int kStagesPerUnit = 256 / KS;
     static constexpr int kChunks = KS / 32;        // 16-byte chunks per row
@@ -1386,6 +1386,7 @@ int launch(int mode, int ntok, const GemmArgs &args, int num_sms, cudaStream_t s
     case kModeNvF16: return launch_mode<kModeNvF16>(args, ntok, num_sms, stream);
     case kModeNvBf16: return launch_mode<kModeNvBf16>(args, ntok, num_sms, stream);
     case kModeMxBf16: return launch_mode<kModeMxBf16>(args, ntok, num_sms, stream);
+    case kModeNvF16N: return launch_mode<kModeNvF16N>(args, ntok, num_sms, stream);
     default: return kLaunchNoKernel;
     }
 }

@@ -7,7 +7,9 @@
 
 namespace petit::gemm {
 
-enum : int { kModeNvF16 = 0, kModeNvBf16 = 1, kModeMxBf16 = 2 };
+// kModeNvF16N: fp16 activations on weights repacked in the fp16-native layout (native nibble
+// order inside a word: cvt.rn.f16x2.e2m1x2 converts a pair with one instruction).
+enum : int { kModeNvF16 = 0, kModeNvBf16 = 1, kModeMxBf16 = 2, kModeNvF16N = 3 };
 enum : int { kLaunchOk = 0, kLaunchBadShape = 1, kLaunchNoKernel = 2, kLaunchCudaError = 3 };
 
 constexpr unsigned kMaxGrid = 160;         // >= SM count of any sm_100 part

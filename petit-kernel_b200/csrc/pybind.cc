@@ -48,8 +48,23 @@ PetitDataType dtype_of(const torch::Tensor &A) {
     return A.dtype() == torch::kBFloat16 ? PETIT_DTYPE_BF16 : PETIT_DTYPE_FP16;
 }
 
+// The packed weight tensor carries its layout in its shape (the tensor is opaque to callers and
+// keeps the reference's dtype and byte count either way): [N/16, 2K] = default layout
+// (fp4.cc:62-63), [N/32, 4K] = fp16-native layout (petit.h, PETIT_WEIGHT_LAYOUT_F16_NATIVE).
+int weight_layout_of(const torch::Tensor &B, int64_t size_n, int64_t size_k) {
+    if (B.dim() == 2 && size_n % 32 == 0 && B.size(0) == size_n / 32 && B.size(1) == 4 * size_k)
+        return PETIT_WEIGHT_LAYOUT_F16_NATIVE;
+    return PETIT_WEIGHT_LAYOUT_DEFAULT;
+}
+
 // ---- fp4.cc:38-78 ------------------------------------------------------------
+torch::Tensor RepackNvFp4Layout(torch::Tensor &b_q_weight, int64_t size_n, int64_t size_k,
+                                const py::object &a_dtype);
 torch::Tensor RepackNvFp4(torch::Tensor &b_q_weight, int64_t size_n, int64_t size_k) {
+    return RepackNvFp4Layout(b_q_weight, size_n, size_k, py::none());
+}
+torch::Tensor RepackNvFp4Layout(torch::Tensor &b_q_weight, int64_t size_n, int64_t size_k,
+                                const py::object &a_dtype) {
     TORCH_CHECK(size_k % kLayoutM == 0, "size_k = ", size_k,
                 " is not divisible by tile_k_size = ", kLayoutM);
     TORCH_CHECK(size_n % kLayoutN == 0, "size_n = ", size_n,
@@ -66,13 +81,23 @@ torch::Tensor RepackNvFp4(torch::Tensor &b_q_weight, int64_t size_n, int64_t siz
     TORCH_CHECK(size_k % kKTile == 0, "size_k = ", size_k,
                 " is not divisible by tile_k_size = ", kKTile);
 
+    // a_dtype = torch.float16: the weights will only ever meet fp16 activations -> fp16-native
+    // layout (needs N % 32 for its shape tag; otherwise, and by default, the layout every
+    // activation type can use)
+    int layout = PETIT_WEIGHT_LAYOUT_DEFAULT;
+    if (!a_dtype.is_none() &&
+        torch::python::detail::py_object_to_dtype(a_dtype) == torch::kFloat16 && size_n % 32 == 0)
+        layout = PETIT_WEIGHT_LAYOUT_F16_NATIVE;
     c10::cuda::CUDAGuard guard(b_q_weight.device());
     auto options = torch::TensorOptions().dtype(b_q_weight.dtype()).device(b_q_weight.device());
     torch::Tensor out =
-        torch::empty({size_n / kLayoutN, size_k * kLayoutN / kPackFactor}, options);
-    int err = petit_repack_fp4_weights(reinterpret_cast<uint32_t *>(out.data_ptr()),
-                                       reinterpret_cast<const uint32_t *>(b_q_weight.data_ptr()),
-                                       size_k, size_n, stream_of(b_q_weight));
+        layout == PETIT_WEIGHT_LAYOUT_F16_NATIVE
+            ? torch::empty({size_n / 32, size_k * 32 / kPackFactor}, options)
+            : torch::empty({size_n / kLayoutN, size_k * kLayoutN / kPackFactor}, options);
+    int err = petit_repack_fp4_weights_layout(
+        reinterpret_cast<uint32_t *>(out.data_ptr()),
+        reinterpret_cast<const uint32_t *>(b_q_weight.data_ptr()), size_k, size_n, layout,
+        stream_of(b_q_weight));
     check_status(err, 0, size_n, size_k, -1);
     return out;
 }
@@ -83,9 +108,10 @@ torch::Tensor UnpackFp4(torch::Tensor &packed, int64_t size_n, int64_t size_k) {
     TORCH_CHECK(packed.numel() == size_n * size_k / kPackFactor, "packed size mismatch");
     c10::cuda::CUDAGuard guard(packed.device());
     torch::Tensor out = torch::empty({size_n, size_k / kPackFactor}, packed.options());
-    int err = petit_unpack_fp4_weights(reinterpret_cast<uint32_t *>(out.data_ptr()),
-                                       reinterpret_cast<const uint32_t *>(packed.data_ptr()),
-                                       size_k, size_n, stream_of(packed));
+    int err = petit_unpack_fp4_weights_layout(
+        reinterpret_cast<uint32_t *>(out.data_ptr()),
+        reinterpret_cast<const uint32_t *>(packed.data_ptr()), size_k, size_n,
+        weight_layout_of(packed, size_n, size_k), stream_of(packed));
     check_status(err, 0, size_n, size_k, -1);
     return out;
 }
@@ -202,9 +228,14 @@ torch::Tensor MulNvFp4A16Impl(const torch::Tensor &A, const torch::Tensor &B, co
     hints.c_type = a_type;
     hints.require_high_precision = 0; // gfx90a workaround (fp4.cc:24-34): n/a on B200
 
-    int err = petit_gemm_nvfp4_a16(c.data_ptr(), A.data_ptr(), B.data_ptr(), s.data_ptr(),
-                                   global_scale.data_ptr<float>(), size_m, size_n, size_k, &hints,
-                                   static_cast<uint64_t>(solution_id), stream_of(A));
+    PetitEpilogue epi = {nullptr, nullptr, PETIT_ACT_NONE, weight_layout_of(B, size_n, size_k)};
+    TORCH_CHECK(epi.weight_layout == PETIT_WEIGHT_LAYOUT_DEFAULT || a_type == PETIT_DTYPE_FP16,
+                "B was repacked for float16 activations (repack_nvfp4(..., a_dtype=torch.float16)); "
+                "A is bfloat16");
+    int err = petit_gemm_nvfp4_a16_ex(c.data_ptr(), A.data_ptr(), B.data_ptr(), s.data_ptr(),
+                                      global_scale.data_ptr<float>(), size_m, size_n, size_k, &hints,
+                                      static_cast<uint64_t>(solution_id), &epi, nullptr,
+                                      stream_of(A));
     check_status(err, size_m, size_n, size_k, solution_id);
     return c;
 }
@@ -318,8 +349,9 @@ torch::Tensor DequantDense(const torch::Tensor &w, const torch::Tensor &scales, 
                      : petit_dequant_mxfp4(out.data_ptr(), w.data_ptr(), scales.data_ptr(),
                                            global_scale, code, size_k, size_n, st);
     else
-        err = packed ? petit_dequant_packed_nvfp4(out.data_ptr(), w.data_ptr(), scales.data_ptr(),
-                                                  global_scale, code, size_k, size_n, st)
+        err = packed ? petit_dequant_packed_nvfp4_layout(out.data_ptr(), w.data_ptr(),
+                                                         scales.data_ptr(), global_scale, code, size_k,
+                                                         size_n, weight_layout_of(w, size_n, size_k), st)
                      : petit_dequant_nvfp4(out.data_ptr(), w.data_ptr(), scales.data_ptr(),
                                            global_scale, code, size_k, size_n, st);
     TORCH_CHECK(err == 0, "dequant hook failed with code ", err,
@@ -331,8 +363,8 @@ torch::Tensor DequantDense(const torch::Tensor &w, const torch::Tensor &scales, 
 
 PYBIND11_MODULE(ops, m) {
     // pybind.cc:9-25 of the reference
-    m.def("repack_nvfp4", &RepackNvFp4, "Repack NVFP4 to Petit FP4", py::arg("qw"),
-          py::arg("size_n"), py::arg("size_k"));
+    m.def("repack_nvfp4", &RepackNvFp4Layout, "Repack NVFP4 to Petit FP4", py::arg("qw"),
+          py::arg("size_n"), py::arg("size_k"), py::arg("a_dtype") = py::none());
     m.def("process_nvfp4_scales", &ProcessNvFp4Scales, "Process NVFP4 scales", py::arg("scales"),
           py::arg("size_n"), py::arg("size_k"));
     m.def("process_mxfp4_scales", &ProcessMxFp4Scales, "Process MXFP4 scales", py::arg("scales"),
@@ -402,7 +434,10 @@ PYBIND11_MODULE(ops, m) {
             c10::cuda::CUDAGuard guard(a.device());
             TORCH_CHECK(!silu_mul || sn % 128 == 0, "silu_mul needs size_n % 128 == 0");
             torch::Tensor c = alloc_or_check_out(out, a, sm, silu_mul ? sn / 2 : sn);
-            PetitEpilogue epi = {nullptr, nullptr, silu_mul ? PETIT_ACT_SILU_MUL : PETIT_ACT_NONE, 0};
+            PetitEpilogue epi = {nullptr, nullptr, silu_mul ? PETIT_ACT_SILU_MUL : PETIT_ACT_NONE,
+                                 mx ? PETIT_WEIGHT_LAYOUT_DEFAULT : weight_layout_of(b, sn, sk)};
+            TORCH_CHECK(epi.weight_layout == PETIT_WEIGHT_LAYOUT_DEFAULT || a_type == PETIT_DTYPE_FP16,
+                        "b was repacked for float16 activations; a is bfloat16");
             if (bias.has_value()) {
                 TORCH_CHECK(bias->is_cuda() && bias->is_contiguous() && bias->numel() == sn &&
                                 bias->scalar_type() == a.scalar_type(),
@@ -430,6 +465,54 @@ PYBIND11_MODULE(ops, m) {
         py::arg("size_m"), py::arg("size_n"), py::arg("size_k"), py::arg("solution_id") = -1,
         py::arg("mx") = false, py::arg("bias") = py::none(), py::arg("residual") = py::none(),
         py::arg("silu_mul") = false);
+
+    // extras: grouped (MoE) GEMM -- tokens sorted by expert, expert g owns rows
+    // [offsets[g], offsets[g + 1]) of a / out; b and s are [E, ...] stacks of repacked experts
+    m.def(
+        "mul_fp4_a16_grouped_out",
+        [](const torch::Tensor &out, const torch::Tensor &a, const torch::Tensor &b,
+           const torch::Tensor &s, const torch::Tensor &gs, const std::vector<int64_t> &offsets,
+           int64_t sn, int64_t sk, int64_t sol, bool mx) {
+            const int64_t e = (int64_t)offsets.size() - 1;
+            TORCH_CHECK(e >= 1 && b.dim() == 3 && s.dim() == 3 && b.size(0) == e && s.size(0) == e,
+                        "b and s must be [num_experts, ...] stacks matching offsets");
+            TORCH_CHECK(a.is_cuda() && a.is_contiguous() && a.dim() == 2 && a.size(1) == sk &&
+                            a.size(0) == offsets.back() && offsets.front() == 0,
+                        "a must be contiguous [total_tokens, size_k] with offsets[-1] rows");
+            TORCH_CHECK(out.is_cuda() && out.is_contiguous() && out.dim() == 2 &&
+                            out.size(0) == a.size(0) && out.size(1) == sn && out.dtype() == a.dtype(),
+                        "out must be contiguous [total_tokens, size_n] in a's dtype");
+            TORCH_CHECK(b.is_cuda() && b.is_contiguous() && s.is_cuda() && s.is_contiguous() &&
+                            b[0].numel() * 4 == sn * sk / 2 && s[0].numel() == sn * sk / (mx ? 32 : 16),
+                        "per-expert packed weight / scale size mismatch");
+            TORCH_CHECK(gs.is_cuda() && gs.scalar_type() == torch::kFloat && gs.numel() == e,
+                        "global_scale must be a float32 CUDA tensor with one entry per expert");
+            PetitDataType a_type = dtype_of(a);
+            c10::cuda::CUDAGuard guard(a.device());
+            std::vector<PetitGroupedProblem> probs((size_t)e);
+            const int64_t esz = a.element_size();
+            for (int64_t g = 0; g < e; ++g) {
+                TORCH_CHECK(offsets[g + 1] >= offsets[g], "offsets must be non-decreasing");
+                probs[g].c = static_cast<char *>(out.data_ptr()) + offsets[g] * sn * esz;
+                probs[g].a = static_cast<const char *>(a.data_ptr()) + offsets[g] * sk * esz;
+                probs[g].b = b[g].data_ptr();
+                probs[g].scales = s[g].data_ptr();
+                probs[g].global_scale_dev = gs.data_ptr<float>() + g;
+                probs[g].m = (unsigned)(offsets[g + 1] - offsets[g]);
+            }
+            PetitSolutionHints hints;
+            hints.a_type = a_type;
+            hints.b_type = mx ? PETIT_DTYPE_MXFP4_E2M1 : PETIT_DTYPE_FP4_E2M1;
+            hints.c_type = a_type;
+            hints.require_high_precision = 0;
+            int err = petit_gemm_fp4_a16_grouped(probs.data(), (unsigned)e, sn, sk, &hints,
+                                                 static_cast<uint64_t>(sol), nullptr, stream_of(a));
+            check_status(err, a.size(0), sn, sk, sol);
+            return out;
+        },
+        py::arg("out"), py::arg("a"), py::arg("b"), py::arg("s"), py::arg("global_scale"),
+        py::arg("offsets"), py::arg("size_n"), py::arg("size_k"), py::arg("solution_id") = -1,
+        py::arg("mx") = false);
 
     // extras: row-parallel GEMM fused with the all-reduce of its output (petit_tp.FusedAllReduce)
     m.def(

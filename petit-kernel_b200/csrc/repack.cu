@@ -29,7 +29,7 @@ namespace {
 constexpr int kThreads = 256;
 
 // ------------------------------------------------------------------ weights
-template <bool kUnpack>
+template <bool kUnpack, bool kNative16 = false>
 __global__ void __launch_bounds__(kThreads)
 repack_weights_kernel(uint4 *__restrict__ out, const uint4 *__restrict__ in, uint32_t size_n,
                       uint32_t size_k) {
@@ -41,7 +41,10 @@ repack_weights_kernel(uint4 *__restrict__ out, const uint4 *__restrict__ in, uin
         const uint32_t ck = (uint32_t)(i % chunks_per_row);
         const size_t native = (size_t)n * chunks_per_row + ck;
         const size_t packed = weight_byte_offset(n, ck * kChunkK, size_n, size_k) / 16;
-        if (kUnpack) {
+        if (kNative16) { // tile arrangement only: the words keep their native nibble order
+            if (kUnpack) out[native] = in[packed];
+            else out[packed] = in[native];
+        } else if (kUnpack) {
             uint4 v = in[packed];
             out[native] = make_uint4(unpack_word(v.x), unpack_word(v.y), unpack_word(v.z),
                                      unpack_word(v.w));
@@ -91,7 +94,8 @@ dequant_dense_kernel(uint32_t *__restrict__ out, const uint8_t *__restrict__ w,
                      const uint8_t *__restrict__ sc, float global_scale, uint32_t size_n,
                      uint32_t size_k) {
     constexpr bool kIsMx = MODE == gemm::kModeMxBf16;
-    constexpr bool kIsBf16 = MODE != gemm::kModeNvF16;
+    constexpr bool kIsBf16 = MODE == gemm::kModeNvBf16 || MODE == gemm::kModeMxBf16;
+    constexpr bool kNative16 = MODE == gemm::kModeNvF16N;
     constexpr uint32_t kGroup = kIsMx ? 32 : 16;
     constexpr uint32_t kScBytes = kIsMx ? 2 : 4;
     const uint32_t chunks_per_row = size_k / kChunkK;
@@ -120,7 +124,8 @@ dequant_dense_kernel(uint32_t *__restrict__ out, const uint8_t *__restrict__ w,
             s1 = kIsMx ? s0 : sc[so + 1];
         } else {
             q = *reinterpret_cast<const uint4 *>(w + (size_t)n * (size_k / 2) + k0 / 2);
-            q = make_uint4(pack_word(q.x), pack_word(q.y), pack_word(q.z), pack_word(q.w));
+            if (!kNative16)
+                q = make_uint4(pack_word(q.x), pack_word(q.y), pack_word(q.z), pack_word(q.w));
             const size_t so = (size_t)n * (size_k / kGroup) + k0 / kGroup;
             s0 = kIsMx ? sc[so] : e4m3_to_e5m3(sc[so]);
             s1 = kIsMx ? s0 : e4m3_to_e5m3(sc[so + 1]);
@@ -152,10 +157,16 @@ bool shape_ok(unsigned size_k, unsigned size_n) {
 }
 
 int weights(void *out, const void *in, unsigned size_k, unsigned size_n, bool unpack,
-            cudaStream_t stream) {
+            cudaStream_t stream, bool native16) {
     if (!shape_ok(size_k, size_n)) return 1;
     const uint64_t total = (uint64_t)size_n * (size_k / kChunkK);
-    if (unpack)
+    if (native16 && unpack)
+        repack_weights_kernel<true, true><<<grid_for(total), kThreads, 0, stream>>>(
+            (uint4 *)out, (const uint4 *)in, size_n, size_k);
+    else if (native16)
+        repack_weights_kernel<false, true><<<grid_for(total), kThreads, 0, stream>>>(
+            (uint4 *)out, (const uint4 *)in, size_n, size_k);
+    else if (unpack)
         repack_weights_kernel<true><<<grid_for(total), kThreads, 0, stream>>>(
             (uint4 *)out, (const uint4 *)in, size_n, size_k);
     else
@@ -204,6 +215,7 @@ int dequant_dense(void *out, const void *w, const void *sc, float global_scale, 
     case gemm::kModeNvF16: PETIT_DQ(gemm::kModeNvF16) break;
     case gemm::kModeNvBf16: PETIT_DQ(gemm::kModeNvBf16) break;
     case gemm::kModeMxBf16: PETIT_DQ(gemm::kModeMxBf16) break;
+    case gemm::kModeNvF16N: PETIT_DQ(gemm::kModeNvF16N) break;
     default: return -1;
     }
 #undef PETIT_DQ

@@ -8,8 +8,9 @@ namespace petit::repack {
 bool shape_ok(unsigned size_k, unsigned size_n);
 
 // 0 ok, 1 bad shape, 3 CUDA error
+// native16: the fp16-native variant of the packed layout (words keep the native nibble order)
 int weights(void *out, const void *in, unsigned size_k, unsigned size_n, bool unpack,
-            cudaStream_t stream);
+            cudaStream_t stream, bool native16 = false);
 int scales(void *out, const void *in, unsigned size_k, unsigned size_n, bool mx, bool unpack,
            cudaStream_t stream);
 // 0 ok, -1 on bad shape / type / launch failure (quantization_utils.cu:619-621)

@@ -60,6 +60,16 @@ def _tag(layer: torch.nn.Module, fmt: str, size_n: int, size_k: int) -> None:
     layer.petit_size_n, layer.petit_size_k = int(size_n), int(size_k)
 
 
+def repack_nvfp4_for(qw: torch.Tensor, size_n: int, size_k: int, a_dtype=None) -> torch.Tensor:
+    """``petit_kernel.repack_nvfp4`` with the activation type the weights will meet.
+    ``a_dtype=torch.float16``: the fp16-native packed layout, whose decode kernel converts a
+    pair of weights with one ``cvt`` + one multiply (the packed tensor stays opaque and keeps
+    its dtype / byte count; ``mul_nvfp4_a16`` recognises the layout from the tensor's shape and
+    rejects bfloat16 activations for it).  ``None`` / bfloat16: the default layout, which every
+    activation type can use."""
+    return ops.repack_nvfp4(qw, size_n, size_k, a_dtype)
+
+
 def interleave_gate_up(t: torch.Tensor) -> torch.Tensor:
     """Row order the fused SiLU * mul epilogue needs (petit.h, PETIT_ACT_SILU_MUL): ``t`` is a
     merged gate_up tensor ``[2 I, ...]`` = gate rows then up rows (weights, block scales or a
@@ -89,7 +99,9 @@ def prepare_nvfp4_layer_for_petit(layer: torch.nn.Module, fuse_silu_mul: bool = 
             layer.bias = torch.nn.Parameter(interleave_gate_up(layer.bias.data), requires_grad=False)
         layer.petit_silu_mul = True
     qweight = layer.weight.view(torch.int32).contiguous()
-    petit_qweight = ops.repack_nvfp4(qweight, part_size_n, part_size_k)
+    # a float16 model gets the fp16-native layout (the layer's activations are params_dtype)
+    a_dtype = torch.float16 if getattr(layer, "params_dtype", None) == torch.float16 else None
+    petit_qweight = ops.repack_nvfp4(qweight, part_size_n, part_size_k, a_dtype)
     layer.weight = torch.nn.Parameter(petit_qweight, requires_grad=False)
     weight_scale = ops.process_nvfp4_scales(layer.weight_scale.data.contiguous(), part_size_n,
                                             part_size_k)

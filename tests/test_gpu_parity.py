@@ -581,6 +581,89 @@ def test_fused_silu_mul_epilogue(pk, dtype, m, inter, k):
                                   None, c, True)
 
 
+@pytest.mark.parametrize("fmt", ["nvfp4", "mxfp4"])
+def test_grouped_moe_gemm(pk, fmt):
+    """petit_gemm_fp4_a16_grouped: token-grouped expert GEMMs (tokens sorted by expert, ragged
+    and empty groups) against the oracle per expert."""
+    e, n, k = 6, 512, 1024
+    counts = [5, 0, 33, 1, 16, 70]
+    offsets = [0]
+    for c in counts:
+        offsets.append(offsets[-1] + c)
+    total = offsets[-1]
+    make = orc.make_nvfp4_case if fmt == "nvfp4" else orc.make_mxfp4_case
+    pack = pack_nvfp4 if fmt == "nvfp4" else pack_mxfp4
+    a_all, bs, ss, gss, refs = [], [], [], [], []
+    for g in range(e):
+        a, q, s, gs = make(max(counts[g], 1), n, k, 100 + g)
+        a = a[:counts[g]]
+        b, sp = pack(pk, q, s, n, k)
+        w = (orc.dequant_nvfp4(q.numpy(), s.view(torch.uint8).numpy()) if fmt == "nvfp4"
+             else orc.dequant_mxfp4(q.numpy(), s.numpy()))
+        refs.append((a.float() @ torch.from_numpy(w).t()) * gs.item())
+        a_all.append(a); bs.append(b); ss.append(sp); gss.append(gs)
+    a_cat = torch.cat(a_all).cuda().contiguous()
+    out = torch.full((total, n), float("nan"), dtype=torch.bfloat16, device="cuda")
+    pk.ops.mul_fp4_a16_grouped_out(out, a_cat, torch.stack(bs), torch.stack(ss),
+                                   torch.cat(gss).cuda(), offsets, n, k, -1, fmt == "mxfp4")
+    torch.cuda.synchronize()
+    assert not torch.isnan(out.float()).any()
+    for g in range(e):
+        if counts[g]:
+            assert orc.max_rel_err(out[offsets[g]:offsets[g + 1]].cpu(), refs[g]) <= GEMM_TOL
+
+
+def test_fp16_native_weight_layout(pk):
+    """repack with a_dtype=float16 -> fp16-native packed layout (cvt.rn.f16x2.e2m1x2 path):
+    round trip bit-exact, exhaustive dequant bit-exact (16 codes x all positive e4m3 scales),
+    GEMM within tolerance on decode / split-tile / prefill shapes, bfloat16 activations rejected,
+    and the glue picks it for float16 layers."""
+    from petit_kernel import petit_utils as pu
+
+    dtype = torch.float16
+    # exhaustive table
+    sb = golden("nvfp4_exhaustive.npz")["scale_bits"]
+    n, k = 128, 2048
+    q = torch.from_numpy(np.repeat(((np.arange(n) % 16).astype(np.uint8) * 0x11)[:, None], k // 2, axis=1).copy())
+    sc = np.tile(np.resize(sb, k // 16), (n, 1))
+    s = torch.from_numpy(sc.copy()).view(torch.float8_e4m3fn)
+    qw = q.cuda().contiguous().view(torch.int32)
+    b16 = pu.repack_nvfp4_for(qw, n, k, torch.float16)
+    assert tuple(b16.shape) == (n // 32, 4 * k) and b16.dtype == torch.int32
+    assert torch.equal(pk.ops.unpack_fp4(b16, n, k), qw)                      # round trip
+    assert not torch.equal(b16.view(-1), pk.repack_nvfp4(qw, n, k).view(-1))  # really another layout
+    sp = pk.process_nvfp4_scales(s.cuda(), n, k)
+    expect = torch.from_numpy(orc.dequant_nvfp4(q.numpy(), sc)).to(dtype)
+    got = pk.ops.dequant_dense(b16, sp, 1.0, dtype, n, k, False, True)
+    assert orc.bits_equal_pm0(got, expect)
+    table = torch.from_numpy(golden("nvfp4_exhaustive.npz")["table"].copy()).to(dtype)
+    assert orc.bits_equal_pm0(got[:16, :126 * 16:16].cpu(), table)
+    # GEMMs: every token-tile width, split tiles, a partial n-tile, prefill
+    for (m, n, k) in ((16, 2048, 4096), (1, 512, 1024), (33, 1056, 768), (64, 1024, 2048),
+                      (300, 1024, 1024), (1024, 2048, 2048)):
+        a, q, s, gs = orc.make_nvfp4_case(m, n, k, 41, dtype=dtype)
+        gs = gs * 0.05  # keep fp16 outputs finite
+        qw = q.cuda().contiguous().view(torch.int32)
+        b16 = pu.repack_nvfp4_for(qw, n, k, torch.float16)
+        sp = pk.process_nvfp4_scales(s.cuda(), n, k)
+        c = pk.mul_nvfp4_a16(a.cuda(), b16, sp, gs.cuda(), m, n, k, -1)
+        w = orc.dequant_nvfp4(q.numpy(), s.view(torch.uint8).numpy())
+        ref32 = (a.float() @ torch.from_numpy(w).t()) * gs.item()
+        assert c.dtype == dtype and orc.max_rel_err(c, ref32) <= GEMM_TOL, (m, n, k)
+        # same result class as the default layout on the same inputs
+        c_def = pk.mul_nvfp4_a16(a.cuda(), pk.repack_nvfp4(qw, n, k), sp, gs.cuda(), m, n, k, -1)
+        assert orc.max_rel_err(c, c_def.float().cpu()) <= GEMM_TOL
+        with pytest.raises(RuntimeError, match="float16 activations"):
+            pk.mul_nvfp4_a16(a.cuda().to(torch.bfloat16), b16, sp, gs.cuda(), m, n, k, -1)
+    # the glue: a float16 layer is prepared in the fp16-native layout
+    lay = _FakeLinear(q, s, n, k)
+    lay.params_dtype = torch.float16
+    pu.prepare_nvfp4_layer_for_petit(lay)
+    assert tuple(lay.weight.shape) == (n // 32, 4 * k)
+    y = pu.apply_petit_nvfp4_linear(a.cuda(), lay.weight, lay.weight_scale, gs.cuda(), n, k)
+    assert orc.max_rel_err(y, ref32) <= GEMM_TOL
+
+
 def test_cpp_source_compat_header_runs_a_gemm(pk, tmp_path):
     """The reference-style C++ unit (tests/native/compat_user.cc over gemm_compat.h) repacks and
     multiplies on the GPU through the namespace-compatible shim and the hal::Device object."""

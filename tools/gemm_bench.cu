@@ -32,7 +32,9 @@ extern "C" void petit_debug_set_trace(unsigned long long *);
 
 int main(int argc, char **argv) {
     bool mx = argc > 1 && !strcmp(argv[1], "mx");
-    bool bf16 = !(argc > 2 && !strcmp(argv[2], "f16"));
+    // "f16" = fp16 activations on default-layout weights, "f16n" = on the fp16-native layout
+    const bool f16n = argc > 2 && !strcmp(argv[2], "f16n");
+    bool bf16 = !(argc > 2 && (!strcmp(argv[2], "f16") || f16n));
     int reps = argc > 3 ? atoi(argv[3]) : 40;
     const char *only = argc > 4 ? argv[4] : "";
     struct Shape { const char *name; unsigned n, k; };
@@ -78,10 +80,12 @@ int main(int argc, char **argv) {
             auto call = [&](int i) {
                 const uint8_t *wp = w + (size_t)(i % copies) * wbytes;
                 const uint8_t *sp = sc + (size_t)(i % copies) * sbytes;
+                PetitEpilogue epi = {nullptr, nullptr, PETIT_ACT_NONE,
+                                     f16n ? PETIT_WEIGHT_LAYOUT_F16_NATIVE : PETIT_WEIGHT_LAYOUT_DEFAULT};
                 int rc = mx ? petit_gemm_mxfp4_a16(c, a, wp, sp, d_gs, m, s.n, s.k, &hints,
                                                    PETIT_SOLUTION_AUTO, nullptr)
-                            : petit_gemm_nvfp4_a16(c, a, wp, sp, d_gs, m, s.n, s.k, &hints,
-                                                   PETIT_SOLUTION_AUTO, nullptr);
+                            : petit_gemm_nvfp4_a16_ex(c, a, wp, sp, d_gs, m, s.n, s.k, &hints,
+                                                      PETIT_SOLUTION_AUTO, &epi, nullptr, nullptr);
                 if (rc) { printf("gemm rc=%d\n", rc); exit(1); }
             };
             int r = m >= 1024 ? std::max(4, reps / 8) : reps;

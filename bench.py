@@ -728,7 +728,29 @@ def sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak, with_competito
         a = torch.randn((16, k), generator=g, device=dev).to(torch.float16)
         us = _timed(lambda i: pk.mul_nvfp4_a16(a, layers[i % copies][idx][4], layers[i % copies][idx][5],
                                                gs, 16, n, k, -1), 20, e0, e1)
-        res["decode_nvfp4_fp16"].append(hbm_row(nm, 16, us))
+        row = hbm_row(nm, 16, us)
+        row["weight_layout"] = "default (bf16-native)"
+        res["decode_nvfp4_fp16"].append(row)
+    # fp16 activations on weights repacked for them (petit_utils.repack_nvfp4_for(..., float16))
+    from petit_kernel import petit_utils as pu
+    for nm, n, k, _, _, _ in layers[0]:
+        ncopy = max(2, int(300e6 // (n * k // 2 + n * k // 16)) + 1)
+        packs = []
+        for _ in range(ncopy):
+            q = torch.randint(0, 256, (n, k // 2), generator=g, dtype=torch.uint8, device=dev)
+            s = (torch.rand((n, k // 16), generator=g, device=dev) * 3.5 + 0.25).to(torch.float8_e4m3fn)
+            packs.append((pu.repack_nvfp4_for(q.view(torch.int32), n, k, torch.float16),
+                          pk.process_nvfp4_scales(s, n, k)))
+            del q, s
+        for m in (1, 16):
+            a = torch.randn((m, k), generator=g, device=dev).to(torch.float16)
+            us = _timed(lambda i: pk.mul_nvfp4_a16(a, packs[i % ncopy][0], packs[i % ncopy][1], gs, m, n, k, -1),
+                        20, e0, e1)
+            row = hbm_row(nm, m, us)
+            row["weight_layout"] = "fp16-native"
+            res["decode_nvfp4_fp16"].append(row)
+        del packs
+        torch.cuda.empty_cache()
     # MXFP4 (config 3): all four shapes, M = 1, 4, 8, 16
     for nm, n, k, _, _, _ in layers[0]:
         ncopy = max(2, int(300e6 // (n * k // 2 + n * k // 32)) + 1)

@@ -71,22 +71,29 @@ bool decode_solution(uint64_t id, Decoded *d) {
 // run the main loop ~17 % faster than 128-token tiles (measured, Llama-70B shapes,
 // M = 512..4096: 82-89 % vs 70-75 % of the bf16 peak) but pay a longer final epilogue
 // and pad M to a multiple of 256, so they are chosen when the padded work still comes
-// out ahead and every SM has enough 256-token units (>= 40) to amortise the tail
-// (o_proj M=512 = 28 units/SM: 58 % with 256 vs 63 % with 128; qkv M=512 = 35: tie).
+// out ahead and every SM has enough 256-token units to amortise the tail.
 int default_ntok(unsigned m, unsigned n, unsigned k) {
     if (const char *e = std::getenv("PETIT_FORCE_NTOK")) {
         int v = std::atoi(e);
         for (int t : kTokVariants)
             if (t == v) return v;
     }
-    for (int t : kTokVariants)
-        if (t <= 128 && m <= (unsigned)t) return t;
     const unsigned long long n_tiles = (n + layout::kTileN - 1) / layout::kTileN;
     const unsigned long long k_tiles = k / layout::kTileK;
+    // Shapes with few (n-tile x k-tile) units per SM (qkv, o_proj: < 28) are bound by the
+    // per-launch tail, not by the main loop: there two or three 64-token tiles beat one 128- or
+    // 256-token tile up to M = 192 (measured, profiles/r02_mid_m_tune.log: qkv M=128 28.9 vs
+    // 32.6 us, M=192 38.7 vs 40.7; o M=192 33.0 vs 37.8).
+    if (m > 64 && m <= 192 && n_tiles * k_tiles < 4096) return 64;
+    for (int t : kTokVariants)
+        if (t <= 128 && m <= (unsigned)t) return t;
     const unsigned long long pad256 = (m + 255ull) / 256 * 256, pad128 = (m + 127ull) / 128 * 128;
     const unsigned long long units256 = n_tiles * (pad256 / 256) * k_tiles;
     const bool faster = pad256 * 85 <= pad128 * 100;
-    return faster && units256 >= 40ull * 148 ? 256 : 128;
+    // (>= 27 units of 256 tokens per SM: o_proj M=512 56.8 us with 256-token tiles vs 62.5 with
+    // 128, qkv 65.7 vs 75.9 -- profiles/r02_mid_m_tune.log; round 1's threshold of 40 predates
+    // the faster exit path)
+    return faster && units256 >= 27ull * 148 ? 256 : 128;
 }
 
 bool problem_shape_ok(unsigned n, unsigned k) {

@@ -193,12 +193,18 @@ def tile_tokens(sol):
 def test_default_solution_rule_is_queryable_on_the_host(lib):
     lib.petit_tune_table_clear()
     h = Hints(BF16, FP4, BF16, 0)
-    expect = {1: 16, 16: 16, 17: 32, 33: 64, 64: 64, 65: 128, 128: 128, 512: 128, 1024: 256}
+    # o_proj (8192 x 8192: few units per SM) keeps 64-token tiles up to M = 192 and takes
+    # 256-token tiles from M = 512; gate_up (57344 x 8192) follows the plain size rule
+    expect = {1: 16, 16: 16, 17: 32, 33: 64, 64: 64, 65: 64, 128: 64, 192: 64, 256: 128, 384: 128,
+              512: 256, 1024: 256}
     for m, ntok in expect.items():
         rc, sol = default_solution(lib, h, m, 8192, 8192)
         assert rc == 0 and tile_tokens(sol) == ntok, (m, ntok, hex(sol))
         rc2, sols = solutions(lib, h, m, 8192, 8192)
         assert sol in sols  # the default is one of the enumerated solutions
+    for m, ntok in {64: 64, 65: 128, 128: 128, 192: 256, 384: 128, 512: 256}.items():
+        rc, sol = default_solution(lib, h, m, 57344, 8192)
+        assert rc == 0 and tile_tokens(sol) == ntok, (m, ntok, hex(sol))
     # error behaviour: unsupported b_type -> -1 (algo_chooser.cc:20-23); bad shape / types -> 1
     assert default_solution(lib, Hints(BF16, INT4, BF16, 0), 16, 8192, 8192)[0] == -1
     assert default_solution(lib, h, 16, 8192, 8192 + 128)[0] == 1

@@ -144,8 +144,7 @@ __device__ __forceinline__ void dequant_chunk(const uint4 q, uint32_t mult, bool
                 out[w * 4 + j] = w < 2 ? hmul2_bcast<false, false>(x[j], mult)
                                        : hmul2_bcast<false, true>(x[j], mult);
         }
-        return;
-    }
+    } else {
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
         uint32_t x[4];
@@ -167,6 +166,7 @@ __device__ __forceinline__ void dequant_chunk(const uint4 q, uint32_t mult, bool
                 out[w * 4 + j] = hmul2_bf16(t, mult);
             }
         }
+    }
     }
 }
 

@@ -57,6 +57,9 @@ using namespace petit::dq;
 #ifndef PETIT_KO
 #define PETIT_KO 0
 #endif
+#ifndef PETIT_PERIODIC
+#define PETIT_PERIODIC 1 // decode dequant loop unrolled over its 3-iteration ring period (0: A/B)
+#endif
 
 namespace {
 
@@ -116,7 +119,12 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     // left next to 227 KB of shared memory: +0.7 us on every reducer's exit path.)
     static constexpr int kPreBytes = 16 * 128 * 4;
     static constexpr int kRingBudget = kSmemBudget - kBarrierBytes - kOutBytes - kPreBytes - 1024;
-    static constexpr int kStages = kRingBudget / kStageBytes > 16 ? 16 : kRingBudget / kStageBytes;
+    static constexpr int kStagesRaw = kRingBudget / kStageBytes > 16 ? 16 : kRingBudget / kStageBytes;
+    // Decode tiles: a ring of exactly 6 stages (2 x the 3 TMEM A stages) makes the ring state of
+    // a dequant group periodic with period 3 iterations, so its loop is unrolled by 3 with every
+    // barrier / shared-memory / TMEM address a constant offset (kPeriodic below).  Six 18 KB
+    // weight stages per SM are 16 MB in flight chip-wide, above the ~10 MB bandwidth-delay product.
+    static constexpr int kStages = (NTOK <= 64 && kStagesRaw >= 6 && kStagesRaw < 12) ? 6 : kStagesRaw;
     // Small-N MMAs that accumulate into the same TMEM columns serialise on the
     // full MMA latency (~130 clk measured), so consecutive k-steps rotate over
     // kChains independent accumulators that the epilogue sums.
@@ -594,13 +602,11 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             const uint32_t sc_lane_off = C::kWBytes + ((c0 / 2) * kTileN + row) * C::kScPerSub +
                                          (c0 & 1) * kScBytesPerChunk;
             const uint32_t st0 = w_base + lane_off, sc0 = w_base + sc_lane_off;
-            // position of this group's first stage
-            uint32_t sidx = group % C::kStages, ph2 = 0, aidx = group % C::kAStages, aph = 1;
-            uint32_t st_w = st0 + sidx * C::kStageBytes, st_sc = sc0 + sidx * C::kStageBytes;
-            uint32_t fb = full_b + sidx * 8, ab = aempty_b + aidx * 8;
-            uint32_t tm = tmem_dst + aidx * C::kACols;
             const bool lane0 = lane == 0;
-            for (uint32_t it = group; it < total; it += kG) {
+            // one stage of this thread: wait for the weights, load, wait for the TMEM slot,
+            // convert + store, hand over
+            auto stage_body = [&](uint32_t st_w, uint32_t st_sc, uint32_t fb, uint32_t ph2, uint32_t ab,
+                                  uint32_t aph, uint32_t tm) {
                 mbar_wait_addr(fb, ph2);
                 uint4 q[kMyChunks];
 #pragma unroll
@@ -661,9 +667,47 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 tc_fence_before();
                 __syncwarp();
                 if (lane0) {
-                    mbar_arrive_addr((uint32_t)((int32_t)ab + kEmptyToFullA)); // a_full[aidx]
-                    mbar_arrive_addr(fb + kFullToEmpty);                        // empty[sidx]
+                    mbar_arrive_addr((uint32_t)((int32_t)ab + kEmptyToFullA)); // a_full[slot]
+                    mbar_arrive_addr(fb + kFullToEmpty);                        // empty[stage]
                 }
+            };
+            constexpr bool kPeriodic = PETIT_PERIODIC && C::kStages == 6 && C::kAStages == 3 && kG == 2;
+            if (kPeriodic) {
+                // Group g takes stages g, g + 2, g + 4, ...: stage index mod 6 and TMEM slot mod 3
+                // repeat every 3 iterations, and the a_empty parity of an iteration depends only
+                // on its position r in that period (use count of the slot = (g + 2r) / 3 + 2q).
+                // So: three copies of the body with constant offsets, one toggling bit.
+                const uint32_t wg = st0 + group * C::kStageBytes, scg = sc0 + group * C::kStageBytes;
+                const uint32_t fbg = full_b + group * 8;
+                uint32_t ab_r[3], ap_r[3], tm_r[3];
+#pragma unroll
+                for (uint32_t r = 0; r < 3; ++r) {
+                    const uint32_t i0 = group + 2 * r, slot = i0 % 3;
+                    ab_r[r] = aempty_b + slot * 8;
+                    ap_r[r] = ((i0 / 3) & 1u) ^ 1u;
+                    tm_r[r] = tmem_dst + slot * C::kACols;
+                }
+                const uint32_t nj = total > group ? (total - group + 1) / 2 : 0;
+                uint32_t j = 0, qpar = 0;
+                for (; j + 3 <= nj; j += 3, qpar ^= 1) {
+#pragma unroll
+                    for (uint32_t r = 0; r < 3; ++r)
+                        stage_body(wg + 2 * r * C::kStageBytes, scg + 2 * r * C::kStageBytes,
+                                   fbg + 2 * r * 8, qpar, ab_r[r], ap_r[r], tm_r[r]);
+                }
+#pragma unroll
+                for (uint32_t r = 0; r < 2; ++r)
+                    if (j + r < nj)
+                        stage_body(wg + 2 * r * C::kStageBytes, scg + 2 * r * C::kStageBytes,
+                                   fbg + 2 * r * 8, qpar, ab_r[r], ap_r[r], tm_r[r]);
+            } else {
+            // position of this group's first stage
+            uint32_t sidx = group % C::kStages, ph2 = 0, aidx = group % C::kAStages, aph = 1;
+            uint32_t st_w = st0 + sidx * C::kStageBytes, st_sc = sc0 + sidx * C::kStageBytes;
+            uint32_t fb = full_b + sidx * 8, ab = aempty_b + aidx * 8;
+            uint32_t tm = tmem_dst + aidx * C::kACols;
+            for (uint32_t it = group; it < total; it += kG) {
+                stage_body(st_w, st_sc, fb, ph2, ab, aph, tm);
                 // step to this group's next stage
                 sidx += kG; st_w += kG * C::kStageBytes; st_sc += kG * C::kStageBytes; fb += kG * 8;
                 if (sidx >= (uint32_t)C::kStages) {
@@ -676,6 +720,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     aidx -= C::kAStages; aph ^= 1;
                     ab -= C::kAStages * 8; tm -= C::kAStages * C::kACols;
                 }
+            }
             }
         } else
         for (uint32_t u = u_begin; u < u_end;) {

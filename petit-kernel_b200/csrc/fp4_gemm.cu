@@ -34,6 +34,7 @@
 
 #include <atomic>
 #include <cstddef>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -1367,6 +1368,19 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     const uint64_t m_tiles = (args.m + NTOK - 1) / NTOK;
     const uint64_t units = (CL ? n_tiles / 2 : n_tiles) * m_tiles * (args.k / kTileK);
     unsigned grid = (unsigned)(units < (uint64_t)num_sms ? units : (uint64_t)num_sms);
+    // Small shards (TP-8 o_proj: 64 tiles x 4 k-tiles on 148 SMs): with < ~2 units per SM every
+    // tile would be cut between CTAs that all finish together, and the split-tile hand-shake
+    // (~2 us) would be most of the launch.  One whole tile per CTA on fewer SMs is faster there
+    // (PETIT_WHOLE_TILES=0 turns the rule off for A/B runs).
+    if (!CL && NTOK <= 64) {
+        static const int whole = [] {
+            const char *e = std::getenv("PETIT_WHOLE_TILES");
+            return e ? std::atoi(e) : 1;
+        }();
+        const uint64_t tiles = n_tiles * m_tiles, k_tiles = args.k / kTileK;
+        if (whole && tiles <= (uint64_t)num_sms && tiles * 3 >= (uint64_t)num_sms && k_tiles <= 6)
+            grid = (unsigned)tiles;
+    }
     if (CL) {
         const uint64_t clusters = units < (uint64_t)(num_sms / 2) ? units : (uint64_t)(num_sms / 2);
         grid = (unsigned)clusters * 2;

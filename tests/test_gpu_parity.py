@@ -395,6 +395,13 @@ def test_gate_up_full_size_properties(pk):
     w = torch.from_numpy(orc.dequant_nvfp4(q.numpy()[rows], s.view(torch.uint8).numpy()[rows]))
     ref = a.float() @ w.t()
     assert orc.max_rel_err(c[:, torch.from_numpy(rows).cuda()], ref) <= GEMM_TOL
+    # the packed dequant hook -- what gpu_ref_f32 builds the large-shape references from -- against
+    # the CPU oracle at full size: sampled rows (every tile position incl. the last tile) bit-exact
+    dense = pk.ops.dequant_dense(b, sp, 1.0, torch.bfloat16, n, k, False, True)
+    rows2 = np.concatenate([rows, np.arange(128), np.arange(n - 128, n)])
+    w2 = torch.from_numpy(orc.dequant_nvfp4(q.numpy()[rows2], s.view(torch.uint8).numpy()[rows2]))
+    assert orc.bits_equal_pm0(dense[torch.from_numpy(rows2).cuda()].cpu(), w2.to(torch.bfloat16))
+    del dense
     # linearity: C(a) + C(a2) == C(a + a2) up to bf16 rounding of three outputs
     a2 = torch.roll(ac, 1, dims=1) * 0.5
     lhs = pk.mul_nvfp4_a16((ac + a2).to(torch.bfloat16), b, sp, gsc, m, n, k, -1).float()

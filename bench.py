@@ -615,6 +615,40 @@ def _timed(fn, reps, e0, e1):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
+def moe_grouped(pk, dev, hbm_peak, e0, e1):
+    rows = []
+    g = torch.Generator(device=dev).manual_seed(11)
+    for name, n, k, counts in (("w13 8 experts", 28672, 4096, [4, 5, 3, 4, 6, 2, 4, 4]),
+                               ("w2 8 experts", 4096, 14336, [4, 5, 3, 4, 6, 2, 4, 4]),
+                               ("w13 8 experts", 28672, 4096, [16, 20, 12, 16, 24, 8, 16, 16]),
+                               ("64 experts 2048x2048", 2048, 2048, [2] * 64)):
+        e = len(counts)
+        stacks = []
+        for _ in range(2):  # two stacks of experts in rotation: > 2x L2 between reuses
+            b = torch.randint(-2 ** 31, 2 ** 31 - 1, (e, n // 16, 2 * k), dtype=torch.int32, device=dev, generator=g)
+            sc = torch.randint(0x30, 0x50, (e, n, k // 16), dtype=torch.uint8, device=dev,
+                               generator=g).view(torch.float8_e4m3fn)
+            stacks.append((b, sc))
+        gs = torch.ones(e, dtype=torch.float32, device=dev)
+        offsets = [0]
+        for c in counts:
+            offsets.append(offsets[-1] + c)
+        a = torch.randn((offsets[-1], k), generator=g, device=dev).to(torch.bfloat16)
+        out = torch.empty((offsets[-1], n), dtype=torch.bfloat16, device=dev)
+        by = sum(1 for c in counts if c) * (n * k // 2 + n * k // 16) + offsets[-1] * (k + n) * 2
+        row = {"case": name, "n": n, "k": k, "tokens_per_expert": counts if e <= 8 else f"{counts[0]} x {e}"}
+        for key, env in (("single_launch", "1"), ("one_by_one", "0")):
+            os.environ["PETIT_GROUPED_SINGLE"] = env
+            us = _timed(lambda i: pk.ops.mul_fp4_a16_grouped_out(out, a, stacks[i % 2][0], stacks[i % 2][1], gs,
+                                                                 offsets, n, k, -1, False), 20, e0, e1)
+            row[key] = {"us": round(us, 2), "gbs": round(by / us * 1e-3), "frac_hbm": round(by / us * 1e-3 / hbm_peak, 3)}
+        os.environ.pop("PETIT_GROUPED_SINGLE", None)
+        rows.append(row)
+        del stacks
+        torch.cuda.empty_cache()
+    return rows
+
+
 def competitors(pk, layers, copies, gs, dev, hbm_peak, tf_peak):
     """Same-box library comparators (the role of the reference bench's
     hipBLASLt backend, tools/benchmarks/matmul/rocm/matmul_hipblaslt.cc:220-263), same CUDA
@@ -767,6 +801,9 @@ def sweep_details(pk, layers, copies, gs, dev, hbm_peak, tf_peak, with_competito
             res["decode_mxfp4_bf16"].append(hbm_row(nm, m, us, 32))
         del packs
         torch.cuda.empty_cache()
+    # grouped (MoE) GEMM, SURVEY section 8 row f4: Mixtral-8x7B-size experts, a decode step's tokens
+    # spread over the experts; one launch for all experts against the experts issued one by one
+    res["moe_grouped_nvfp4_bf16"] = moe_grouped(pk, dev, hbm_peak, e0, e1)
     # prefill after the decode rows: it power-caps the part, and the decode kernels are
     # issue-bound (clock-sensitive).  The denominator is the BURST bf16 peak, so every shape
     # starts from an idle part (1 s pause): back to back the sweep runs into the 1 kW power cap

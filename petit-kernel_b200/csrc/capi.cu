@@ -282,7 +282,7 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
               const float *global_scale_dev, unsigned m, unsigned n, unsigned k,
               const PetitSolutionHints *hints, uint64_t solution_id, bool force_mx,
               cudaStream_t stream, const PetitFusedAllReduce *ar = nullptr,
-              const PetitEpilogue *epi = nullptr) {
+              const PetitEpilogue *epi = nullptr, const gemm::GroupTable *table = nullptr) {
     if (ar) {
         // every rank must take part in every call: no early-out on empty shapes
         if (m == 0 || n == 0 || k == 0 || m > gemm::kArMaxTokens) return PETIT_ERROR_PROBLEM_SHAPE;
@@ -425,7 +425,8 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
             return PETIT_ERROR_KERNEL_SHAPE;
         mode = gemm::kModeNvF16N;
     }
-    switch (gemm::launch(mode, d.ntok, args, num_sms, stream)) {
+    switch (table ? gemm::launch_grouped(mode, d.ntok, args, *table, num_sms, stream)
+                  : gemm::launch(mode, d.ntok, args, num_sms, stream)) {
     case gemm::kLaunchOk: return PETIT_OK;
     case gemm::kLaunchBadShape: return PETIT_ERROR_PROBLEM_SHAPE;
     case gemm::kLaunchNoKernel: return PETIT_ERROR_KERNEL_SHAPE;
@@ -505,12 +506,85 @@ int petit_gemm_fp4_a16_grouped(const PetitGroupedProblem *problems, unsigned num
     if (!hints) return PETIT_ERROR_KERNEL_SHAPE;
     if (epilogue && epilogue->residual) return PETIT_ERROR_PROBLEM_SHAPE; // per-group shapes differ
     const bool mx = hints->b_type == PETIT_DTYPE_MXFP4_E2M1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    // One launch for all groups when the groups' activations and outputs are consecutive row
+    // blocks of one tensor (tokens sorted by expert), the token tile is a decode tile and the
+    // tile table fits the kernel parameters; otherwise the groups are issued back to back.
+    // PETIT_GROUPED_SINGLE=0 forces the second form (A/B runs, tests).
+    const char *single_env = std::getenv("PETIT_GROUPED_SINGLE");
+    const bool plain_epi = !epilogue || (!epilogue->bias && !epilogue->residual);
+    const bool silu = epilogue && epilogue->activation == PETIT_ACT_SILU_MUL;
+    const size_t out_n = silu ? n / 2 : n;
+    if (!(single_env && std::atoi(single_env) == 0) && plain_epi && n != 0 && k != 0) {
+        const size_t esz = 2; // fp16 / bf16
+        const PetitGroupedProblem *first = nullptr, *prev = nullptr;
+        unsigned max_m = 0, live = 0;
+        uint64_t total_rows = 0;
+        bool contiguous = true;
+        for (unsigned g = 0; g < num_groups && contiguous; ++g) {
+            const PetitGroupedProblem &p = problems[g];
+            if (p.m == 0) continue;
+            if (!first) first = &p;
+            if (prev && (static_cast<const char *>(p.a) !=
+                             static_cast<const char *>(prev->a) + (size_t)prev->m * k * esz ||
+                         static_cast<char *>(p.c) != static_cast<char *>(prev->c) + (size_t)prev->m * out_n * esz))
+                contiguous = false;
+            if (((reinterpret_cast<uintptr_t>(p.b) | reinterpret_cast<uintptr_t>(p.scales)) & 15) ||
+                !p.global_scale_dev)
+                contiguous = false; // let the per-group path report it
+            prev = &p;
+            max_m = p.m > max_m ? p.m : max_m;
+            total_rows += p.m;
+            ++live;
+        }
+        int ntok = 0;
+        uint64_t sid = solution_id;
+        if (contiguous && live > 1 && total_rows < (1ull << 31)) {
+            if (solution_id == PETIT_SOLUTION_AUTO) {
+                if (hints->a_type == PETIT_DTYPE_FP16 || hints->a_type == PETIT_DTYPE_BF16) {
+                    ntok = max_m <= 16 ? 16 : (max_m <= 32 ? 32 : 64);
+                    sid = make_solution(ntok, mx ? kElemMx : kElemNv,
+                                        hints->a_type == PETIT_DTYPE_BF16 ? kMfmaBf16 : kMfmaF16);
+                }
+            } else {
+                Decoded d;
+                if (decode_solution(solution_id, &d) && d.ntok <= 64) ntok = d.ntok;
+            }
+        }
+        if (ntok) {
+            gemm::GroupTable table;
+            table.tiles = 0;
+            table.pad = 0;
+            uint32_t row = 0;
+            bool fits = true;
+            for (unsigned g = 0; g < num_groups && fits; ++g) {
+                const PetitGroupedProblem &p = problems[g];
+                for (unsigned r = 0; r < p.m; r += (unsigned)ntok) {
+                    if (table.tiles == gemm::kMaxGroupTiles) {
+                        fits = false;
+                        break;
+                    }
+                    gemm::GroupEntry &e = table.e[table.tiles++];
+                    e.w = static_cast<const uint8_t *>(p.b);
+                    e.sc = static_cast<const uint8_t *>(p.scales);
+                    e.gs = p.global_scale_dev;
+                    e.row0 = row + r;
+                    e.rows = p.m - r < (unsigned)ntok ? p.m - r : (unsigned)ntok;
+                }
+                row += p.m;
+            }
+            if (fits)
+                return gemm_impl(first->c, first->a, first->b, first->scales, first->global_scale_dev,
+                                 (unsigned)total_rows, n, k, hints, sid, mx, st, nullptr, epilogue,
+                                 &table);
+        }
+    }
     for (unsigned g = 0; g < num_groups; ++g) {
         const PetitGroupedProblem &p = problems[g];
         if (p.m == 0) continue;
         const int rc = gemm_impl(p.c, p.a, p.b, p.scales, p.global_scale_dev, p.m, n, k, hints,
-                                 solution_id, mx, reinterpret_cast<cudaStream_t>(stream), nullptr,
-                                 epilogue);
+                                 solution_id, mx, st, nullptr, epilogue);
         if (rc != PETIT_OK) return rc;
     }
     return PETIT_OK;

@@ -330,11 +330,22 @@ __device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
 // traffic that bounds the prefill kernel (measured 42.7 B/clk/SM, the L2 fabric cap).
 // AR = true: the instantiation whose epilogue also all-reduces the output over NVLink (separate
 // so that the plain GEMM's register allocation is untouched by the exchange code).
-template <int MODE, int NTOK, int KS, bool CL, bool AR = false>
+// GR = true: the grouped (MoE) instantiation -- token tile t of the schedule is row block
+// table.e[t] of the concatenated activations and multiplies that entry's weights.
+struct NoGroups {};
+template <bool GR> struct GroupParam { using type = NoGroups; };
+template <> struct GroupParam<true> { using type = GroupTable; };
+__device__ __forceinline__ const GroupEntry &group_entry(const GroupTable &t, uint32_t i) { return t.e[i]; }
+__device__ __forceinline__ GroupEntry group_entry(const NoGroups &, uint32_t) { return GroupEntry{}; }
+__device__ __forceinline__ uint32_t group_tiles(const GroupTable &t) { return t.tiles; }
+__device__ __forceinline__ uint32_t group_tiles(const NoGroups &) { return 0; }
+
+template <int MODE, int NTOK, int KS, bool CL, bool AR = false, bool GR = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                 const __grid_constant__ CUtensorMap tmap_out,
-                const __grid_constant__ GemmArgs args) {
+                const __grid_constant__ GemmArgs args,
+                const __grid_constant__ typename GroupParam<GR>::type table) {
     using C = Cfg<MODE, NTOK, KS>;
     uint32_t cta_rank = 0;
     if (CL) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -365,7 +376,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
     sched.k_tiles = args.k / kTileK;
     sched.n_tiles = (args.n + kTileN - 1) / kTileN;
     if (CL) sched.n_tiles /= 2; // unit space counts n-tile PAIRS (launcher ensures even)
-    sched.m_tiles = (args.m + NTOK - 1) / NTOK;
+    sched.m_tiles = GR ? group_tiles(table) : (args.m + NTOK - 1) / NTOK;
     sched.total_units = sched.k_tiles * sched.n_tiles * sched.m_tiles;
     sched.grid = CL ? gridDim.x / 2 : gridDim.x;
     sched.n_mul = CL ? 2 : 1;
@@ -440,9 +451,17 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         for (uint32_t u = u_begin; u < u_end;) {
             const Segment g = make_segment(sched, u, u_end);
             const uint32_t rows = tile_rows(args.n, g.n_tile);
-            const uint8_t *w_tile = args.w + (size_t)g.n_tile * kTileN * k_bytes_half;
+            const uint8_t *w_base = args.w, *sc_base = args.sc;
+            uint32_t tok0 = g.m_tile * NTOK; // first token row of the tile
+            if (GR) {
+                const GroupEntry &ge = group_entry(table, g.m_tile);
+                w_base = ge.w;
+                sc_base = ge.sc;
+                tok0 = ge.row0;
+            }
+            const uint8_t *w_tile = w_base + (size_t)g.n_tile * kTileN * k_bytes_half;
             const uint8_t *sc_tile =
-                args.sc + (size_t)g.n_tile * kTileN * (args.k / 64) * C::kScPerSub;
+                sc_base + (size_t)g.n_tile * kTileN * (args.k / 64) * C::kScPerSub;
             const uint32_t w_stage_bytes = C::kChunks * rows * 16;
             const uint32_t sc_stage_bytes = C::kSubs * rows * C::kScPerSub;
             const uint32_t n_stage = (g.kt1 - g.kt0) * C::kStagesPerUnit;
@@ -485,11 +504,10 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                                 tma_load_3d_mc(st + sl * (NTOK * 128) +
                                                    cta_rank * (NTOK / 2) * 128,
                                                &tmap_act, &bars->full_act[s], 0,
-                                               g.m_tile * NTOK + cta_rank * (NTOK / 2),
+                                               tok0 + cta_rank * (NTOK / 2),
                                                k_slab + sl, (uint16_t)3);
                         } else
-                            tma_load_3d(st, &tmap_act, &bars->full_act[s], 0, g.m_tile * NTOK,
-                                        k_slab);
+                            tma_load_3d(st, &tmap_act, &bars->full_act[s], 0, tok0, k_slab);
                     }
                 }
                 __syncwarp();
@@ -811,7 +829,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
         const uint32_t row = quarter * 32 + lane;
         const uint32_t lane_base = (quarter * 32) << 16;
         griddep_wait(); // global_scale, workspace and C may depend on the previous kernel
-        float gs = *args.global_scale;
+        float gs = GR ? 0.f : *args.global_scale;
         gs *= epilogue_factor<MODE>(); // power of two folded out of the A operand
         uint32_t ar_epoch = 0;
         if (AR)
@@ -825,8 +843,14 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
             const uint32_t acc = seg % C::kNumAcc;
             const uint32_t acc_ph = (seg / C::kNumAcc) & 1;
             const bool full_k = g.kt0 == 0 && g.kt1 == sched.k_tiles;
-            const uint32_t m0 = g.m_tile * NTOK;
-            const uint32_t m_valid = args.m - m0 < (uint32_t)NTOK ? args.m - m0 : NTOK;
+            uint32_t m0 = g.m_tile * NTOK;
+            uint32_t m_valid = args.m - m0 < (uint32_t)NTOK ? args.m - m0 : NTOK;
+            if (GR) { // this tile's row block and its group's scale
+                const GroupEntry &ge = group_entry(table, g.m_tile);
+                m0 = ge.row0;
+                m_valid = ge.rows;
+                gs = __ldg(ge.gs) * epilogue_factor<MODE>();
+            }
 
             // Split tiles (stream-K): the CTA that owns the FIRST k-part of a tile
             // reaches it as the last segment of its range, after every other
@@ -1234,7 +1258,15 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     }
                     fence_proxy_async();
                     named_bar_sync(team_bar, kNumEpilogueWarps * 32);
-                    if (ew_tid == 0) {
+                    if (GR && m_valid - (uint32_t)c0 < 16u) {
+                        // (grouped: the rows behind the group's last token are another group's)
+                        const uint32_t j = ew_tid / 8, chunk = ew_tid % 8;
+                        if ((uint32_t)c0 + j < m_valid)
+                            *reinterpret_cast<uint4 *>(static_cast<uint16_t *>(args.c) +
+                                                       (size_t)(m0 + c0 + j) * (args.n / 2) +
+                                                       g.n_tile * 64 + chunk * 8) =
+                                *reinterpret_cast<const uint4 *>(stg + j * 64 + chunk * 8);
+                    } else if (ew_tid == 0) {
                         // tmap_out describes c[m, n / 2] with [16][64] boxes in this mode
                         tma_store_2d(&tmap_out, stg, (int)(g.n_tile * 64), (int)(m0 + c0));
                         bulk_commit_group();
@@ -1252,7 +1284,19 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     if (ew_tid == 0 && !PETIT_DBG(args.debug_flags, 128u))
                         bulk_wait_group_read<C::kOutBufs - 2>();
                     named_bar_sync(team_bar, kNumEpilogueWarps * 32);
-                    if (ew_tid == 0 && !PETIT_DBG(args.debug_flags, 512u)) {
+                    if (GR && m_valid - (uint32_t)c0 < 16u) {
+                        // the rows behind a group's last token belong to the next group: no
+                        // TMA box here, 16-byte stores of the valid tokens only (a thread takes
+                        // chunk ew_tid % 16 of tokens ew_tid / 16 and + 8)
+                        const uint32_t chunk = ew_tid % 16;
+#pragma unroll
+                        for (uint32_t j = ew_tid / 16; j < 16; j += 8)
+                            if ((uint32_t)c0 + j < m_valid && chunk * 8 < rows)
+                                *reinterpret_cast<uint4 *>(
+                                    static_cast<uint16_t *>(args.c) + (size_t)(m0 + c0 + j) * args.n +
+                                    g.n_tile * kTileN + chunk * 8) =
+                                    *reinterpret_cast<const uint4 *>(stg + j * kTileN + chunk * 8);
+                    } else if (ew_tid == 0 && !PETIT_DBG(args.debug_flags, 512u)) {
                         tma_store_2d(&tmap_out, stg, (int)(g.n_tile * kTileN), (int)(m0 + c0));
                         bulk_commit_group();
                     }
@@ -1323,8 +1367,9 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int MODE, int NTOK, int KS, bool CL = false, bool AR = false>
-int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
+template <int MODE, int NTOK, int KS, bool CL = false, bool AR = false, bool GR = false>
+int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream,
+                   const GroupTable *table = nullptr) {
     using C = Cfg<MODE, NTOK, KS>;
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) return kLaunchCudaError;
@@ -1355,7 +1400,7 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return kLaunchCudaError;
 
     static std::atomic<bool> attr_set[64]; // per instantiation, per device (zero-initialised)
-    auto kern = fp4_gemm_kernel<MODE, NTOK, KS, CL, AR>;
+    auto kern = fp4_gemm_kernel<MODE, NTOK, KS, CL, AR, GR>;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return kLaunchCudaError;
     if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
@@ -1365,7 +1410,7 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
         attr_set[dev & 63].store(true, std::memory_order_release);
     }
     const uint64_t n_tiles = (args.n + kTileN - 1) / kTileN;
-    const uint64_t m_tiles = (args.m + NTOK - 1) / NTOK;
+    const uint64_t m_tiles = GR ? table->tiles : (args.m + NTOK - 1) / NTOK;
     const uint64_t units = (CL ? n_tiles / 2 : n_tiles) * m_tiles * (args.k / kTileK);
     unsigned grid = (unsigned)(units < (uint64_t)num_sms ? units : (uint64_t)num_sms);
     // Small shards (TP-8 o_proj: 64 tiles x 4 k-tiles on 148 SMs): with < ~2 units per SM every
@@ -1401,8 +1446,22 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream) {
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CL ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_out, args);
+    cudaError_t e;
+    if constexpr (GR)
+        e = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_out, args, *table);
+    else
+        e = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_out, args, NoGroups{});
     return e == cudaSuccess ? kLaunchOk : kLaunchCudaError;
+}
+
+template <int MODE> int launch_grouped_mode(const GemmArgs &args, int ntok, const GroupTable &table,
+                                            int num_sms, cudaStream_t stream) {
+    switch (ntok) {
+    case 16: return launch_variant<MODE, 16, 256, false, false, true>(args, num_sms, stream, &table);
+    case 32: return launch_variant<MODE, 32, 256, false, false, true>(args, num_sms, stream, &table);
+    case 64: return launch_variant<MODE, 64, 256, false, false, true>(args, num_sms, stream, &table);
+    default: return kLaunchNoKernel;
+    }
 }
 
 template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
@@ -1439,6 +1498,20 @@ size_t workspace_partials_bytes() {
     return (size_t)kMaxGrid * kTileN * 256 * sizeof(float);
 }
 size_t workspace_counters_bytes() { return ((size_t)kMaxTiles + 1) * sizeof(unsigned); }
+
+int launch_grouped(int mode, int ntok, const GemmArgs &args, const GroupTable &table, int num_sms,
+                   cudaStream_t stream) {
+    if (table.tiles == 0 || table.tiles > kMaxGroupTiles || args.ar_world > 1 || args.bias ||
+        args.residual)
+        return kLaunchBadShape;
+    switch (mode) {
+    case kModeNvF16: return launch_grouped_mode<kModeNvF16>(args, ntok, table, num_sms, stream);
+    case kModeNvBf16: return launch_grouped_mode<kModeNvBf16>(args, ntok, table, num_sms, stream);
+    case kModeMxBf16: return launch_grouped_mode<kModeMxBf16>(args, ntok, table, num_sms, stream);
+    case kModeNvF16N: return launch_grouped_mode<kModeNvF16N>(args, ntok, table, num_sms, stream);
+    default: return kLaunchNoKernel;
+    }
+}
 
 int launch(int mode, int ntok, const GemmArgs &args, int num_sms, cudaStream_t stream) {
     switch (mode) {

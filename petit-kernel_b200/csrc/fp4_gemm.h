@@ -54,10 +54,33 @@ inline size_t ar_recv_bytes(unsigned n) {
     return (size_t)2 * kArMaxWorld * ((n + 127) / 128) * (kArMaxTokens / 16) * kArSlotBytes;
 }
 
+// Grouped (MoE) GEMM in one launch: the activations / outputs of all groups are the row
+// blocks of ONE [total_rows, k] / [total_rows, n] tensor (tokens sorted by expert), and the
+// unit space of the stream-K schedule runs over the token tiles of all groups; entry t says
+// which rows token tile t covers and whose weights it multiplies.
+struct GroupEntry {
+    const uint8_t *w;   // packed weights of the tile's group
+    const uint8_t *sc;  // packed scales
+    const float *gs;    // the group's global scale (device)
+    uint32_t row0;      // first row of the tile in the concatenated activations / output
+    uint32_t rows;      // valid rows (1 .. ntok)
+};
+constexpr unsigned kMaxGroupTiles = 96; // 3 KB of kernel parameters
+struct GroupTable {
+    uint32_t tiles;
+    uint32_t pad;
+    GroupEntry e[kMaxGroupTiles];
+};
+
 size_t workspace_partials_bytes();
 size_t workspace_counters_bytes(); // kMaxTiles counters + the status word (last)
 
 // ntok: tokens per MMA (16, 32, 64, 128, 256).
 int launch(int mode, int ntok, const GemmArgs &args, int num_sms, cudaStream_t stream);
+// args.a / args.c: the concatenated tensors, args.m: their rows; args.w / sc / global_scale
+// are ignored (per tile in `table`); ntok 16, 32 or 64; SiLU * mul is the only fused epilogue
+// (no bias / residual: they would be per group), no all-reduce.
+int launch_grouped(int mode, int ntok, const GemmArgs &args, const GroupTable &table, int num_sms,
+                   cudaStream_t stream);
 
 } // namespace petit::gemm

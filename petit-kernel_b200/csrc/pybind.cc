@@ -472,16 +472,18 @@ PYBIND11_MODULE(ops, m) {
         "mul_fp4_a16_grouped_out",
         [](const torch::Tensor &out, const torch::Tensor &a, const torch::Tensor &b,
            const torch::Tensor &s, const torch::Tensor &gs, const std::vector<int64_t> &offsets,
-           int64_t sn, int64_t sk, int64_t sol, bool mx) {
+           int64_t sn, int64_t sk, int64_t sol, bool mx, bool silu_mul) {
             const int64_t e = (int64_t)offsets.size() - 1;
             TORCH_CHECK(e >= 1 && b.dim() == 3 && s.dim() == 3 && b.size(0) == e && s.size(0) == e,
                         "b and s must be [num_experts, ...] stacks matching offsets");
             TORCH_CHECK(a.is_cuda() && a.is_contiguous() && a.dim() == 2 && a.size(1) == sk &&
                             a.size(0) == offsets.back() && offsets.front() == 0,
                         "a must be contiguous [total_tokens, size_k] with offsets[-1] rows");
+            TORCH_CHECK(!silu_mul || sn % 128 == 0, "silu_mul needs size_n % 128 == 0");
+            const int64_t out_n = silu_mul ? sn / 2 : sn;
             TORCH_CHECK(out.is_cuda() && out.is_contiguous() && out.dim() == 2 &&
-                            out.size(0) == a.size(0) && out.size(1) == sn && out.dtype() == a.dtype(),
-                        "out must be contiguous [total_tokens, size_n] in a's dtype");
+                            out.size(0) == a.size(0) && out.size(1) == out_n && out.dtype() == a.dtype(),
+                        "out must be contiguous [total_tokens, size_n (/ 2 with silu_mul)] in a's dtype");
             TORCH_CHECK(b.is_cuda() && b.is_contiguous() && s.is_cuda() && s.is_contiguous() &&
                             b[0].numel() * 4 == sn * sk / 2 && s[0].numel() == sn * sk / (mx ? 32 : 16),
                         "per-expert packed weight / scale size mismatch");
@@ -493,7 +495,7 @@ PYBIND11_MODULE(ops, m) {
             const int64_t esz = a.element_size();
             for (int64_t g = 0; g < e; ++g) {
                 TORCH_CHECK(offsets[g + 1] >= offsets[g], "offsets must be non-decreasing");
-                probs[g].c = static_cast<char *>(out.data_ptr()) + offsets[g] * sn * esz;
+                probs[g].c = static_cast<char *>(out.data_ptr()) + offsets[g] * out_n * esz;
                 probs[g].a = static_cast<const char *>(a.data_ptr()) + offsets[g] * sk * esz;
                 probs[g].b = b[g].data_ptr();
                 probs[g].scales = s[g].data_ptr();
@@ -505,14 +507,16 @@ PYBIND11_MODULE(ops, m) {
             hints.b_type = mx ? PETIT_DTYPE_MXFP4_E2M1 : PETIT_DTYPE_FP4_E2M1;
             hints.c_type = a_type;
             hints.require_high_precision = 0;
+            PetitEpilogue epi = {nullptr, nullptr, silu_mul ? PETIT_ACT_SILU_MUL : PETIT_ACT_NONE,
+                                 mx ? PETIT_WEIGHT_LAYOUT_DEFAULT : weight_layout_of(b[0], sn, sk)};
             int err = petit_gemm_fp4_a16_grouped(probs.data(), (unsigned)e, sn, sk, &hints,
-                                                 static_cast<uint64_t>(sol), nullptr, stream_of(a));
+                                                 static_cast<uint64_t>(sol), &epi, stream_of(a));
             check_status(err, a.size(0), sn, sk, sol);
             return out;
         },
         py::arg("out"), py::arg("a"), py::arg("b"), py::arg("s"), py::arg("global_scale"),
         py::arg("offsets"), py::arg("size_n"), py::arg("size_k"), py::arg("solution_id") = -1,
-        py::arg("mx") = false);
+        py::arg("mx") = false, py::arg("silu_mul") = false);
 
     // extras: row-parallel GEMM fused with the all-reduce of its output (petit_tp.FusedAllReduce)
     m.def(

@@ -591,33 +591,98 @@ def test_fused_silu_mul_epilogue(pk, dtype, m, inter, k):
 @pytest.mark.parametrize("fmt", ["nvfp4", "mxfp4"])
 def test_grouped_moe_gemm(pk, fmt):
     """petit_gemm_fp4_a16_grouped: token-grouped expert GEMMs (tokens sorted by expert, ragged
-    and empty groups) against the oracle per expert."""
-    e, n, k = 6, 512, 1024
-    counts = [5, 0, 33, 1, 16, 70]
+    and empty groups) against the oracle per expert.  The single-launch grouped kernel (one
+    stream-K schedule over the token tiles of all experts) must agree with the same GEMMs issued
+    one by one (PETIT_GROUPED_SINGLE=0; the two cut the k range at different places, so they
+    agree to an output ulp, not bit for bit), on whole and on split tiles, for every decode tile
+    width, and must not touch the rows of a neighbouring expert."""
+    make = orc.make_nvfp4_case if fmt == "nvfp4" else orc.make_mxfp4_case
+    pack = pack_nvfp4 if fmt == "nvfp4" else pack_mxfp4
+    for (n, k, counts) in ((512, 1024, [5, 0, 33, 1, 16, 70]),        # 64-token tiles, 2 for the last
+                           (2048, 4096, [3, 1, 0, 7, 2, 16, 4, 1]),   # 16-token tiles, split by stream-K
+                           (1040 // 16 * 16, 768, [17, 32, 0, 0, 9]),  # 32-token tiles, partial n-tile
+                           (256, 256, [1] * 100)):                    # > 96 tiles: issued one by one
+        e = len(counts)
+        offsets = [0]
+        for c in counts:
+            offsets.append(offsets[-1] + c)
+        total = offsets[-1]
+        if fmt == "mxfp4":
+            n = (n + 31) // 32 * 32
+        a_all, bs, ss, gss, refs = [], [], [], [], []
+        for g in range(e):
+            a, q, s, gs = make(max(counts[g], 1), n, k, 100 + g)
+            a = a[:counts[g]]
+            if g < 8 or not bs:
+                b, sp = pack(pk, q, s, n, k)
+                w = (orc.dequant_nvfp4(q.numpy(), s.view(torch.uint8).numpy()) if fmt == "nvfp4"
+                     else orc.dequant_mxfp4(q.numpy(), s.numpy()))
+                wt = torch.from_numpy(w).t()
+            else:  # many experts: reuse the 8th expert's weights, own activations and scale
+                b, sp = bs[7], ss[7]
+            refs.append((a.float() @ wt) * gs.item())
+            a_all.append(a); bs.append(b); ss.append(sp); gss.append(gs)
+        a_cat = torch.cat(a_all).cuda().contiguous()
+        outs = []
+        for single in ("1", "0"):
+            os.environ["PETIT_GROUPED_SINGLE"] = single
+            try:
+                out = torch.full((total, n), float("nan"), dtype=torch.bfloat16, device="cuda")
+                pk.ops.mul_fp4_a16_grouped_out(out, a_cat, torch.stack(bs), torch.stack(ss),
+                                               torch.cat(gss).cuda(), offsets, n, k, -1, fmt == "mxfp4")
+                torch.cuda.synchronize()
+            finally:
+                os.environ.pop("PETIT_GROUPED_SINGLE", None)
+            assert not torch.isnan(out.float()).any()
+            outs.append(out)
+        scale = outs[1].float().abs().max().item()
+        assert (outs[0].float() - outs[1].float()).abs().max().item() <= scale * 2 ** -7, (n, k, counts)
+        for g in range(e):
+            if counts[g]:
+                assert orc.max_rel_err(outs[0][offsets[g]:offsets[g + 1]].cpu(), refs[g]) <= GEMM_TOL
+        assert pk.ops.workspace_status() == 0
+
+
+def test_grouped_moe_silu_mul(pk):
+    """Grouped GEMM with the fused SiLU * mul epilogue (an MoE MLP's w13 in one launch): against
+    the unfused grouped output of the same packed weights, rows interleaved per 128-row tile
+    (columns [128 t, 128 t + 64) gate, [128 t + 64, 128 t + 128) up).  Ragged groups: the stores
+    behind a group's last token must not reach the next group's rows."""
+    n, k, counts = 1024, 2048, [3, 0, 17, 1, 16, 5]
     offsets = [0]
     for c in counts:
         offsets.append(offsets[-1] + c)
-    total = offsets[-1]
-    make = orc.make_nvfp4_case if fmt == "nvfp4" else orc.make_mxfp4_case
-    pack = pack_nvfp4 if fmt == "nvfp4" else pack_mxfp4
-    a_all, bs, ss, gss, refs = [], [], [], [], []
+    total, e = offsets[-1], len(counts)
+    bs, ss, gss, a_all = [], [], [], []
     for g in range(e):
-        a, q, s, gs = make(max(counts[g], 1), n, k, 100 + g)
-        a = a[:counts[g]]
-        b, sp = pack(pk, q, s, n, k)
-        w = (orc.dequant_nvfp4(q.numpy(), s.view(torch.uint8).numpy()) if fmt == "nvfp4"
-             else orc.dequant_mxfp4(q.numpy(), s.numpy()))
-        refs.append((a.float() @ torch.from_numpy(w).t()) * gs.item())
-        a_all.append(a); bs.append(b); ss.append(sp); gss.append(gs)
+        a, q, s, gs = orc.make_nvfp4_case(max(counts[g], 1), n, k, 300 + g)
+        b, sp = pack_nvfp4(pk, q, s, n, k)
+        bs.append(b); ss.append(sp); gss.append(gs * 0.02); a_all.append(a[:counts[g]])
     a_cat = torch.cat(a_all).cuda().contiguous()
-    out = torch.full((total, n), float("nan"), dtype=torch.bfloat16, device="cuda")
-    pk.ops.mul_fp4_a16_grouped_out(out, a_cat, torch.stack(bs), torch.stack(ss),
-                                   torch.cat(gss).cuda(), offsets, n, k, -1, fmt == "mxfp4")
-    torch.cuda.synchronize()
-    assert not torch.isnan(out.float()).any()
-    for g in range(e):
-        if counts[g]:
-            assert orc.max_rel_err(out[offsets[g]:offsets[g + 1]].cpu(), refs[g]) <= GEMM_TOL
+    b, sp, gsc = torch.stack(bs), torch.stack(ss), torch.cat(gss).cuda()
+    plain = torch.empty((total, n), dtype=torch.bfloat16, device="cuda")
+    pk.ops.mul_fp4_a16_grouped_out(plain, a_cat, b, sp, gsc, offsets, n, k, -1, False)
+    t = plain.view(total, n // 128, 2, 64).float()
+    want = (torch.nn.functional.silu(t[:, :, 0]).to(torch.bfloat16).float() * t[:, :, 1]).to(torch.bfloat16)
+    want = want.reshape(total, n // 2)
+    for single in ("1", "0"):
+        os.environ["PETIT_GROUPED_SINGLE"] = single
+        try:
+            got = torch.full((total, n // 2), float("nan"), dtype=torch.bfloat16, device="cuda")
+            pk.ops.mul_fp4_a16_grouped_out(got, a_cat, b, sp, gsc, offsets, n, k, -1, False, True)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("PETIT_GROUPED_SINGLE", None)
+        assert not torch.isnan(got.float()).any()
+        # the unfused reference came from another k split: allow an output ulp on top of expf's
+        diff = (got.float() - want.float()).abs()
+        tol = want.float().abs() * 2 ** -5 + plain.float().abs().max().item() * 2 ** -7
+        assert bool((diff <= tol).all()), (single, diff.max().item())
+        if single == "1":
+            assert (got == want).float().mean().item() > 0.95
+    with pytest.raises(RuntimeError):
+        pk.ops.mul_fp4_a16_grouped_out(torch.empty((total, n), dtype=torch.bfloat16, device="cuda"),
+                                       a_cat, b, sp, gsc, offsets, n, k, -1, False, True)
 
 
 def test_fp16_native_weight_layout(pk):

@@ -386,7 +386,10 @@ int gemm_impl(void *c, const void *a, const void *b, const void *scales,
         const bool can_two_shot = ar->world == 4 || ar->world == 8 || ar->world == 2;
         args.ar_two_shot = !can_two_shot ? 0u
                            : two_shot_env >= 0 ? (uint32_t)(two_shot_env != 0)
-                                               : (ar->world > 2 ? 1u : 0u);
+                                               : (ar->world > 4 ? 1u : 0u);
+        // (measured, M = 16 layer set: world 4 one-shot 63.6 us per step vs two-shot 68.3 -- one
+        // hop instead of two, 24 KB of packets per CTA; at world 8 the 56 KB per CTA cost more
+        // than the second hop)
         args.ar_rank = (uint32_t)ar->rank;
         args.ar_state = static_cast<unsigned *>(ar->state);
         for (int r = 0; r < ar->world; ++r) args.ar_recv[r] = static_cast<uint8_t *>(ar->recv[r]);

@@ -1061,8 +1061,8 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
                     // write is needed -- into the destination rank's receive buffer
                     // [parity][source rank][slot]; ranks' values are always added in rank order
                     // in fp32, so every rank ends up with the same bits.
-                    //  one-shot (world <= 2): push the partial to every peer, sum all partials.
-                    //  two-shot (world 4 or 8): reduce-scatter + all-gather inside every tile --
+                    //  one-shot (world <= 4): push the partial to every peer, sum all partials.
+                    //  two-shot (world 8): reduce-scatter + all-gather inside every tile --
                     //    rank r reduces rows [r * 128 / world, (r + 1) * 128 / world) of EVERY
                     //    tile: a thread pushes its row's partial to the row's reducer and waits
                     //    for the finished row, the reducer's threads sum the peers' partials and

@@ -33,6 +33,12 @@
 #include "sm100_ptx.cuh"
 
 #include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
 #include <cstddef>
 #include <cstdlib>
 #include <cuda_bf16.h>
@@ -191,13 +197,17 @@ struct Sched {
     uint32_t total_units; // < 2^31, checked by the launcher
     uint32_t grid;
     uint32_t n_mul, n_add; // this CTA's n-tile = n_mul * (tile / m_tiles) + n_add
+    const int8_t *adj;     // GemmArgs::cut_adj (kernel parameter space)
 
     __device__ __forceinline__ uint32_t begin(uint32_t b) const {
-        return (uint32_t)((uint64_t)total_units * b / grid);
+        return (uint32_t)((int32_t)((uint64_t)total_units * b / grid) + (int32_t)adj[b]);
     }
-    // CTA that owns unit u (inverse of begin()).
+    // CTA that owns unit u (inverse of begin()): the equal-range owner, corrected for the cuts.
     __device__ __forceinline__ uint32_t owner(uint32_t u) const {
-        return (uint32_t)((((uint64_t)u + 1) * grid - 1) / total_units);
+        uint32_t o = (uint32_t)((((uint64_t)u + 1) * grid - 1) / total_units);
+        while (o > 0 && begin(o) > u) --o;
+        while (o + 1 < grid && begin(o + 1) <= u) ++o;
+        return o;
     }
 };
 
@@ -381,6 +391,7 @@ fp4_gemm_kernel(const __grid_constant__ CUtensorMap tmap_act,
     sched.grid = CL ? gridDim.x / 2 : gridDim.x;
     sched.n_mul = CL ? 2 : 1;
     sched.n_add = cta_rank;
+    sched.adj = args.cut_adj;
     const uint32_t u_begin = sched.begin(sched_id);
     const uint32_t u_end = sched.begin(sched_id + 1);
 
@@ -1367,6 +1378,91 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// Stream-K range cuts (decode tiles).  With equal ranges, a CTA whose whole range lies inside
+// one output tile publishes its partial at the very end of its run -- exactly when the CTA that
+// reduces the tile (the owner of the tile's first k-part, which meets the tile LAST) wants it:
+// the reducer then sits through publish + poll + read (~2 us, most of the tail of qkv / o /
+// down at M <= 16, profiles/r02_percta_summary.txt).  Model: a unit costs 1, a partial is usable
+// `lat` units after its segment ended; a local search over the cut points minimises the largest
+// modelled finish time (then the sum of squares), i.e. contributors that a reducer waits for get
+// shorter ranges and the others the units they give up.  Result cached per (units, k_tiles,
+// grid, lat); adj[b] = cut[b] - units * b / grid.  PETIT_TILT_UNITS=0 turns it off.
+struct CutKey {
+    uint32_t units, k_tiles, grid;
+    int lat;
+    bool operator<(const CutKey &o) const {
+        return std::tie(units, k_tiles, grid, lat) < std::tie(o.units, o.k_tiles, o.grid, o.lat);
+    }
+};
+struct CutAdj { int8_t v[kMaxGrid + 4]; };
+
+void tilt_cuts(uint32_t units, uint32_t k_tiles, uint32_t grid, int lat, int8_t *adj) {
+    static std::mutex mu;
+    static std::map<CutKey, CutAdj> cache;
+    const CutKey key{units, k_tiles, grid, lat};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            std::memcpy(adj, it->second.v, sizeof(it->second.v));
+            return;
+        }
+    }
+    std::vector<int64_t> base(grid + 1), cut(grid + 1);
+    for (uint32_t b = 0; b <= grid; ++b) cut[b] = base[b] = (int64_t)((uint64_t)units * b / grid);
+    // modelled finish time of every CTA -> (max, sum of squares)
+    auto eval = [&](const std::vector<int64_t> &c, int64_t *worst, int64_t *sumsq) {
+        *worst = 0;
+        *sumsq = 0;
+        for (uint32_t i = 0; i < grid; ++i) {
+            const int64_t len = c[i + 1] - c[i];
+            int64_t fin = len;
+            if (len > 0) {
+                const int64_t head = (c[i + 1] - 1) / k_tiles * k_tiles, tile_end = head + k_tiles;
+                if (head >= c[i] && tile_end > c[i + 1]) // reducer of a tile that goes on
+                    for (uint32_t j = i + 1; j < grid && c[j] < tile_end; ++j) {
+                        const int64_t seg_end = (c[j + 1] < tile_end ? c[j + 1] : tile_end) - c[j];
+                        if (seg_end + lat > fin) fin = seg_end + lat;
+                    }
+            }
+            if (fin > *worst) *worst = fin;
+            *sumsq += fin * fin;
+        }
+    };
+    int64_t worst, sumsq;
+    eval(cut, &worst, &sumsq);
+    for (int iter = 0; iter < 400; ++iter) {
+        int best_b = -1, best_d = 0;
+        int64_t bw = worst, bs = sumsq;
+        for (uint32_t b = 1; b < grid; ++b)
+            for (int d = -1; d <= 1; d += 2) {
+                const int64_t nc = cut[b] + d;
+                if (nc < cut[b - 1] + 1 || nc > cut[b + 1] - 1 || nc - base[b] > 100 || nc - base[b] < -100)
+                    continue;
+                cut[b] = nc;
+                int64_t w, sq;
+                eval(cut, &w, &sq);
+                cut[b] = nc - d;
+                if (w < bw || (w == bw && sq < bs)) {
+                    bw = w;
+                    bs = sq;
+                    best_b = (int)b;
+                    best_d = d;
+                }
+            }
+        if (best_b < 0) break;
+        cut[best_b] += best_d;
+        worst = bw;
+        sumsq = bs;
+    }
+    CutAdj out;
+    std::memset(out.v, 0, sizeof(out.v));
+    for (uint32_t b = 0; b <= grid; ++b) out.v[b] = (int8_t)(cut[b] - base[b]);
+    std::memcpy(adj, out.v, sizeof(out.v));
+    std::lock_guard<std::mutex> lock(mu);
+    cache[key] = out;
+}
+
 template <int MODE, int NTOK, int KS, bool CL = false, bool AR = false, bool GR = false>
 int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream,
                    const GroupTable *table = nullptr) {
@@ -1446,11 +1542,22 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream,
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CL ? 2 : 1;
+    GemmArgs largs = args;
+    std::memset(largs.cut_adj, 0, sizeof(largs.cut_adj));
+    if (!CL && NTOK <= 64 && grid > 1 && units > grid) {
+        static const int lat_env = [] {
+            const char *e = std::getenv("PETIT_TILT_UNITS");
+            return e ? std::atoi(e) : -1;
+        }();
+        const int lat = lat_env >= 0 ? lat_env : (NTOK <= 32 ? 5 : 3);
+        if (lat > 0)
+            tilt_cuts((uint32_t)units, (uint32_t)(args.k / kTileK), grid, lat, largs.cut_adj);
+    }
     cudaError_t e;
     if constexpr (GR)
-        e = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_out, args, *table);
+        e = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_out, largs, *table);
     else
-        e = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_out, args, NoGroups{});
+        e = cudaLaunchKernelEx(&cfg, kern, tmap, tmap_out, largs, NoGroups{});
     return e == cudaSuccess ? kLaunchOk : kLaunchCudaError;
 }
 

@@ -35,6 +35,10 @@ struct GemmArgs {
     uint32_t use_pdl;       // launch with programmatic stream serialisation
     uint32_t skew_cycles;   // initial phase skew between k-slice warps (tuning knob)
     unsigned long long *trace; // optional [grid][16] globaltimer stamps (debug), else null
+    // Stream-K range cuts: CTA b owns units [total * b / grid + cut_adj[b], total * (b + 1) / grid
+    // + cut_adj[b + 1]).  All zero = equal ranges; the launcher shortens the ranges of CTAs that a
+    // split-tile reducer would otherwise wait for (fp4_gemm.cu, tilt_cuts).
+    int8_t cut_adj[kMaxGrid + 4];
     // Fused all-reduce of a row-parallel (K-split) GEMM over NVLink peer memory (ar_world > 1):
     // the CTA that finishes an output tile pushes its 16-bit partial to every peer's receive
     // buffer as self-validating {data, epoch} packets and sums the peers' packets of the same

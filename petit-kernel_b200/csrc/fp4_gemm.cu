@@ -13,7 +13,8 @@
 //    tensor-core rows and each weight is dequantised exactly once per tile.
 //  * TS-form MMA: dequantised weights never touch shared memory.  One dequant
 //    thread owns one weight row = one TMEM lane: it reads 16 bytes (32 fp4) per
-//    ld.shared, converts with cvt.rn.f16x2.e2m1x2 (+ HMUL2 by the block scale),
+//    ld.shared, converts (bit placement for the bf16-native layout, cvt.rn.f16x2.e2m1x2
+//    for the fp16-native one, + HMUL2 by the block scale: dequant.cuh),
 //    and writes the 16-bit pairs straight into the A-operand columns of TMEM
 //    with tcgen05.st.  The MMA reads A from TMEM and the token tile (B operand)
 //    from 128B-swizzled shared memory filled by TMA.
@@ -24,9 +25,14 @@
 //    whatever the shape.  Tiles cut by a range boundary are reduced through an
 //    fp32 workspace by the CTA that owns the tile's first k-part (a static choice: it
 //    reaches the tile last, at the end of its range), in CTA order (bit-reproducible).
+//    For decode tiles the ranges are not exactly equal: CTAs a reducer would wait for get
+//    slightly shorter ones (tilt_cuts).
 //  * warp roles: 2 TMA producers (weights / token tiles), 1 MMA issuer (2 for decode
 //    tiles, each owning half of the accumulator chains), 16 dequant warps, 4 epilogue
 //    warps; accumulators are double-buffered in TMEM so the epilogue overlaps the next tile.
+//  * instantiations of the same kernel: CL (2-CTA cluster, token tile multicast, prefill),
+//    AR (epilogue all-reduces the tile over NVLink peer memory, row-parallel TP layers),
+//    GR (grouped / MoE: the token tiles of all experts in one schedule).
 #include "fp4_gemm.h"
 #include "dequant.cuh"
 #include "layout.cuh"

@@ -38,6 +38,7 @@
 #include "layout.cuh"
 #include "sm100_ptx.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstring>
@@ -355,6 +356,10 @@ __device__ __forceinline__ const GroupEntry &group_entry(const GroupTable &t, ui
 __device__ __forceinline__ GroupEntry group_entry(const NoGroups &, uint32_t) { return GroupEntry{}; }
 __device__ __forceinline__ uint32_t group_tiles(const GroupTable &t) { return t.tiles; }
 __device__ __forceinline__ uint32_t group_tiles(const NoGroups &) { return 0; }
+
+// the grouped instantiation's parameters must fit the classic 4 KB kernel-parameter space
+static_assert(2 * sizeof(CUtensorMap) + sizeof(GemmArgs) + sizeof(GroupTable) <= 4096,
+              "kernel parameters of the grouped GEMM exceed 4 KB: shrink kMaxGroupTiles");
 
 template <int MODE, int NTOK, int KS, bool CL, bool AR = false, bool GR = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -1414,30 +1419,37 @@ void tilt_cuts(uint32_t units, uint32_t k_tiles, uint32_t grid, int lat, int8_t 
             return;
         }
     }
-    std::vector<int64_t> base(grid + 1), cut(grid + 1);
+    std::vector<int64_t> base(grid + 1), cut(grid + 1), fin(grid), pre(grid + 1), suf(grid + 2), tmp;
     for (uint32_t b = 0; b <= grid; ++b) cut[b] = base[b] = (int64_t)((uint64_t)units * b / grid);
-    // modelled finish time of every CTA -> (max, sum of squares)
-    auto eval = [&](const std::vector<int64_t> &c, int64_t *worst, int64_t *sumsq) {
-        *worst = 0;
-        *sumsq = 0;
-        for (uint32_t i = 0; i < grid; ++i) {
-            const int64_t len = c[i + 1] - c[i];
-            int64_t fin = len;
-            if (len > 0) {
-                const int64_t head = (c[i + 1] - 1) / k_tiles * k_tiles, tile_end = head + k_tiles;
-                if (head >= c[i] && tile_end > c[i + 1]) // reducer of a tile that goes on
-                    for (uint32_t j = i + 1; j < grid && c[j] < tile_end; ++j) {
-                        const int64_t seg_end = (c[j + 1] < tile_end ? c[j + 1] : tile_end) - c[j];
-                        if (seg_end + lat > fin) fin = seg_end + lat;
-                    }
-            }
-            if (fin > *worst) *worst = fin;
-            *sumsq += fin * fin;
+    // modelled finish time of CTA i
+    auto fin_of = [&](uint32_t i) {
+        const int64_t len = cut[i + 1] - cut[i];
+        int64_t f = len;
+        if (len > 0) {
+            const int64_t head = (cut[i + 1] - 1) / k_tiles * k_tiles, tile_end = head + k_tiles;
+            if (head >= cut[i] && tile_end > cut[i + 1]) // reducer of a tile that goes on
+                for (uint32_t j = i + 1; j < grid && cut[j] < tile_end; ++j) {
+                    const int64_t seg_end = (cut[j + 1] < tile_end ? cut[j + 1] : tile_end) - cut[j];
+                    if (seg_end + lat > f) f = seg_end + lat;
+                }
         }
+        return f;
     };
-    int64_t worst, sumsq;
-    eval(cut, &worst, &sumsq);
     for (int iter = 0; iter < 400; ++iter) {
+        int64_t worst = 0, sumsq = 0, min_len = units;
+        for (uint32_t i = 0; i < grid; ++i) {
+            fin[i] = fin_of(i);
+            sumsq += fin[i] * fin[i];
+            min_len = std::min(min_len, cut[i + 1] - cut[i]);
+        }
+        pre[0] = 0;
+        for (uint32_t i = 0; i < grid; ++i) pre[i + 1] = std::max(pre[i], fin[i]);
+        suf[grid] = suf[grid + 1] = 0;
+        for (uint32_t i = grid; i-- > 0;) suf[i] = std::max(suf[i + 1], fin[i]);
+        worst = pre[grid];
+        // moving cut b changes CTAs b - 1 and b and the reducers that count them as contributors:
+        // at most `span` CTAs back
+        const uint32_t span = (uint32_t)std::min<int64_t>(grid, k_tiles / std::max<int64_t>(min_len, 1) + 2);
         int best_b = -1, best_d = 0;
         int64_t bw = worst, bs = sumsq;
         for (uint32_t b = 1; b < grid; ++b)
@@ -1445,9 +1457,14 @@ void tilt_cuts(uint32_t units, uint32_t k_tiles, uint32_t grid, int lat, int8_t 
                 const int64_t nc = cut[b] + d;
                 if (nc < cut[b - 1] + 1 || nc > cut[b + 1] - 1 || nc - base[b] > 100 || nc - base[b] < -100)
                     continue;
+                const uint32_t lo = b > span ? b - span : 0;
                 cut[b] = nc;
-                int64_t w, sq;
-                eval(cut, &w, &sq);
+                int64_t w = std::max(pre[lo], suf[b + 1]), sq = sumsq;
+                for (uint32_t i = lo; i <= b; ++i) {
+                    const int64_t f = fin_of(i);
+                    w = std::max(w, f);
+                    sq += f * f - fin[i] * fin[i];
+                }
                 cut[b] = nc - d;
                 if (w < bw || (w == bw && sq < bs)) {
                     bw = w;
@@ -1458,8 +1475,6 @@ void tilt_cuts(uint32_t units, uint32_t k_tiles, uint32_t grid, int lat, int8_t 
             }
         if (best_b < 0) break;
         cut[best_b] += best_d;
-        worst = bw;
-        sumsq = bs;
     }
     CutAdj out;
     std::memset(out.v, 0, sizeof(out.v));
@@ -1550,7 +1565,7 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream,
     cfg.numAttrs = CL ? 2 : 1;
     GemmArgs largs = args;
     std::memset(largs.cut_adj, 0, sizeof(largs.cut_adj));
-    if (!CL && NTOK <= 64 && grid > 1 && units > grid) {
+    if (!CL && NTOK <= 64 && grid > 1 && units >= 4ull * grid) {
         static const int lat_env = [] {
             const char *e = std::getenv("PETIT_TILT_UNITS");
             return e ? std::atoi(e) : -1;

@@ -159,6 +159,91 @@ static void run_case(bool mx, bool bf16, unsigned m, unsigned n, unsigned k, int
     cudaFree(d_a); cudaFree(d_c); cudaFree(d_dense); cudaFree(d_dense2); cudaFree(d_gs);
 }
 
+// Grouped (MoE) GEMM through the C ABI: `groups` experts with their own weights, ragged token
+// counts.  contiguous = the experts' rows are consecutive blocks of one tensor (one launch);
+// otherwise every expert's rows start at a padded offset (the per-expert path).  Both against
+// the C oracle per expert; rows outside the groups must stay untouched (0xffff).
+static void run_grouped(bool contiguous, unsigned n, unsigned k, const std::vector<unsigned> &counts) {
+    const unsigned groups = (unsigned)counts.size(), pad = contiguous ? 0 : 3;
+    std::vector<std::vector<uint8_t>> q(groups), sc(groups);
+    std::vector<uint8_t *> d_qp(groups), d_scp(groups);
+    std::vector<float> gs(groups);
+    float *d_gs;
+    CK(cudaMalloc(&d_gs, groups * 4));
+    unsigned total = 0;
+    std::vector<unsigned> row0(groups);
+    for (unsigned g = 0; g < groups; ++g) {
+        row0[g] = total;
+        total += counts[g] + (counts[g] ? pad : 0);
+        q[g].resize((size_t)n * k / 2);
+        sc[g].resize((size_t)n * k / 16);
+        for (auto &b : q[g]) b = (uint8_t)rnd();
+        for (auto &x : sc[g]) x = (uint8_t)(0x20 + rnd() % 0x30);
+        gs[g] = rnd_uniform(0.5f, 1.5f);
+        uint8_t *d_q, *d_sc;
+        CK(cudaMalloc(&d_q, q[g].size()));
+        CK(cudaMalloc(&d_sc, sc[g].size()));
+        CK(cudaMalloc(&d_qp[g], q[g].size()));
+        CK(cudaMalloc(&d_scp[g], sc[g].size()));
+        CK(cudaMemcpy(d_q, q[g].data(), q[g].size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_sc, sc[g].data(), sc[g].size(), cudaMemcpyHostToDevice));
+        int rc = petit_repack_fp4_weights((uint32_t *)d_qp[g], (const uint32_t *)d_q, k, n, nullptr);
+        rc |= petit_repack_nvfp4_scales(d_scp[g], d_sc, k, n, nullptr);
+        if (rc) { printf("FAIL grouped repack rc=%d\n", rc); ++g_fail; return; }
+        CK(cudaDeviceSynchronize());
+        cudaFree(d_q); cudaFree(d_sc);
+    }
+    CK(cudaMemcpy(d_gs, gs.data(), groups * 4, cudaMemcpyHostToDevice));
+    std::vector<uint16_t> a((size_t)total * k);
+    std::vector<float> af(a.size());
+    for (size_t i = 0; i < a.size(); ++i) {
+        a[i] = petit_oracle_f32_to_bf16(rnd_uniform(-2.f, 2.f));
+        af[i] = petit_oracle_bf16_to_f32(a[i]);
+    }
+    uint16_t *d_a, *d_c;
+    CK(cudaMalloc(&d_a, a.size() * 2));
+    CK(cudaMalloc(&d_c, (size_t)total * n * 2));
+    CK(cudaMemcpy(d_a, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_c, 0xff, (size_t)total * n * 2));
+    std::vector<PetitGroupedProblem> probs(groups);
+    for (unsigned g = 0; g < groups; ++g)
+        probs[g] = {d_c + (size_t)row0[g] * n, d_a + (size_t)row0[g] * k, d_qp[g], d_scp[g], d_gs + g, counts[g]};
+    PetitSolutionHints hints = {PETIT_DTYPE_BF16, PETIT_DTYPE_FP4_E2M1, PETIT_DTYPE_BF16, 0};
+    int grc = petit_gemm_fp4_a16_grouped(probs.data(), groups, n, k, &hints, PETIT_SOLUTION_AUTO, nullptr, nullptr);
+    cudaError_t e = cudaDeviceSynchronize();
+    int st = -1;
+    petit_workspace_status(nullptr, &st);
+    std::vector<uint16_t> c((size_t)total * n);
+    CK(cudaMemcpy(c.data(), d_c, c.size() * 2, cudaMemcpyDeviceToHost));
+    double worst = 0;
+    size_t touched = 0;
+    std::vector<float> wf((size_t)n * k);
+    for (unsigned g = 0; g < groups; ++g) {
+        if (!counts[g]) continue;
+        petit_oracle_dequant_nvfp4(wf.data(), q[g].data(), sc[g].data(), n, k);
+        std::vector<float> cref((size_t)counts[g] * n);
+        petit_oracle_gemm_f32(cref.data(), af.data() + (size_t)row0[g] * k, wf.data(), counts[g], n, k);
+        double max_err = 0, max_ref = 0;
+        for (size_t i = 0; i < cref.size(); ++i) {
+            const double ref = cref[i] * gs[g];
+            const double got = petit_oracle_bf16_to_f32(c[(size_t)row0[g] * n + i]);
+            const double err = fabs(got - ref);
+            if (err > max_err || std::isnan(err)) max_err = std::isnan(err) ? 1e30 : err;
+            if (fabs(ref) > max_ref) max_ref = fabs(ref);
+        }
+        worst = fmax(worst, max_err / (max_ref > 0 ? max_ref : 1));
+        for (size_t i = 0; i < (size_t)pad * n; ++i) // the padding rows behind the group
+            touched += c[(size_t)(row0[g] + counts[g]) * n + i] != 0xffff;
+    }
+    const bool ok = grc == 0 && e == cudaSuccess && st == 0 && worst <= 1e-2 && touched == 0;
+    printf("%s grouped %s n=%u k=%u groups=%u tokens=%u rc=%d ws_status=%d max_rel=%.3e touched_outside=%zu\n",
+           ok ? "PASS" : "FAIL", contiguous ? "one-launch" : "per-expert", n, k, groups, total, grc, st, worst,
+           touched);
+    if (!ok) ++g_fail;
+    for (unsigned g = 0; g < groups; ++g) { cudaFree(d_qp[g]); cudaFree(d_scp[g]); }
+    cudaFree(d_a); cudaFree(d_c); cudaFree(d_gs);
+}
+
 int main(int argc, char **argv) {
     setvbuf(stdout, nullptr, _IOLBF, 0); // progress survives a timeout kill
     bool full = argc > 1 && !strcmp(argv[1], "full");
@@ -177,6 +262,9 @@ int main(int argc, char **argv) {
         run_case(false, false, 7, 2048, 512, t, 1.0f, false);
     }
     run_case(false, true, 300, 1040, 768, 0, 1.0f, false);
+    run_grouped(true, 1024, 2048, {3, 0, 17, 1, 16, 5, 40});
+    run_grouped(false, 1024, 2048, {3, 0, 17, 1, 16, 5, 40});
+    run_grouped(true, 528, 512, {1, 1, 2, 16});
     run_case(false, true, 566, 4096, 1024, 0, 1.0f, false);
     if (full) {
         run_case(false, true, 16, 10240, 8192, 0, 1.0f, true);

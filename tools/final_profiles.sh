@@ -8,13 +8,14 @@ B=tools/gemm_bench
 timeout 600 python -m pytest tests -m gpu -x -q --timeout 200 > $OUT/pytest_gpu.log 2>&1
 echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
 timeout 100 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1
-timeout 400 python bench.py > $OUT/bench_n1.json 2> $OUT/bench_n1.err
+timeout 600 python bench.py > $OUT/bench_n1.json 2> $OUT/bench_n1.err
 timeout 100 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference_arm.json 2> $OUT/bench_reference_arm.err
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file $OUT/ncu_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-details > $OUT/ncu_launches.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fp4_gemm -s 12 -c 4 -f -o $OUT/layerset \
   python bench.py --steps 1 --warmup 3 --no-details > $OUT/ncu_full.log 2>&1
 ncu -i $OUT/layerset.ncu-rep --page raw --csv > $OUT/ncu_full_layerset_raw.csv 2>/dev/null
+rm -f $OUT/layerset.ncu-rep   # (gpurun_out/ may not exceed 64 MiB; the raw page is what profiles/ keeps)
 for s in qkv o gate_up down; do
   PETIT_TRACE2=1 PETIT_TRACE_DUMP=$OUT/percta_70b.csv timeout 60 $B nv bf16 40 $s 16
 done > $OUT/trace_decode.log 2>&1

@@ -1389,28 +1389,44 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// Stream-K range cuts (decode tiles).  With equal ranges, a CTA whose whole range lies inside
-// one output tile publishes its partial at the very end of its run -- exactly when the CTA that
-// reduces the tile (the owner of the tile's first k-part, which meets the tile LAST) wants it:
-// the reducer then sits through publish + poll + read (~2 us, most of the tail of qkv / o /
-// down at M <= 16, profiles/r02_percta_summary.txt).  Model: a unit costs 1, a partial is usable
-// `lat` units after its segment ended; a local search over the cut points minimises the largest
-// modelled finish time (then the sum of squares), i.e. contributors that a reducer waits for get
-// shorter ranges and the others the units they give up.  Result cached per (units, k_tiles,
-// grid, lat); adj[b] = cut[b] - units * b / grid.  PETIT_TILT_UNITS=0 turns it off.
+// Stream-K range cuts (decode tiles): equal ranges do not finish together, for two reasons.
+//  (1) Roles.  A CTA whose whole range lies inside one output tile publishes its partial at the
+//      very end of its run -- exactly when the CTA that reduces the tile (the owner of the tile's
+//      first k-part, which meets the tile LAST) wants it: the reducer then sits through publish
+//      + poll + read (~2 us, most of the tail of qkv / o / down at M <= 16).
+//  (2) Arrival.  Behind another grid (programmatic dependent launch) the CTAs become resident in
+//      block-id order over ~3 us as the previous grid drains; until griddepcontrol.wait returns
+//      they dequantise ahead (smem ring + TMEM A stages = ~4.5 units), so the last block ids
+//      start with up to that much less done and finish last (profiles/r02_percta_summary.txt:
+//      dequant_done +0.5 / +0.9 / +1.9 us for block ids 112.. / 128.. / 144.. on qkv).
+// Model (quarter units): CTA i starts at start[i] = late * profile(i / grid), a unit costs 1,
+// a partial is usable `lat` units after its segment ended.  The cuts start from the
+// water-filling solution for start[] and a local search over single-unit moves of the cut
+// points minimises the largest modelled finish time (then the sum of squares).  Result cached
+// per (units, k_tiles, grid, lat, late); adj[b] = cut[b] - units * b / grid.
+// PETIT_TILT_UNITS / PETIT_TILT_LATE (units; 0 = off) override lat / late.
 struct CutKey {
     uint32_t units, k_tiles, grid;
-    int lat;
+    int lat, late;
     bool operator<(const CutKey &o) const {
-        return std::tie(units, k_tiles, grid, lat) < std::tie(o.units, o.k_tiles, o.grid, o.lat);
+        return std::tie(units, k_tiles, grid, lat, late) <
+               std::tie(o.units, o.k_tiles, o.grid, o.lat, o.late);
     }
 };
 struct CutAdj { int8_t v[kMaxGrid + 4]; };
 
-void tilt_cuts(uint32_t units, uint32_t k_tiles, uint32_t grid, int lat, int8_t *adj) {
+// share of the head start a CTA at relative block id r lacks (measured, see above)
+double late_profile(double r) {
+    const double xs[] = {0.0, 0.6, 0.8, 0.92, 1.0}, ys[] = {0.0, 0.0, 0.2, 0.5, 1.0};
+    for (int i = 1; i < 5; ++i)
+        if (r <= xs[i]) return ys[i - 1] + (ys[i] - ys[i - 1]) * (r - xs[i - 1]) / (xs[i] - xs[i - 1]);
+    return 1.0;
+}
+
+void tilt_cuts(uint32_t units, uint32_t k_tiles, uint32_t grid, int lat, int late, int8_t *adj) {
     static std::mutex mu;
     static std::map<CutKey, CutAdj> cache;
-    const CutKey key{units, k_tiles, grid, lat};
+    const CutKey key{units, k_tiles, grid, lat, late};
     {
         std::lock_guard<std::mutex> lock(mu);
         auto it = cache.find(key);
@@ -1419,18 +1435,39 @@ void tilt_cuts(uint32_t units, uint32_t k_tiles, uint32_t grid, int lat, int8_t 
             return;
         }
     }
-    std::vector<int64_t> base(grid + 1), cut(grid + 1), fin(grid), pre(grid + 1), suf(grid + 2), tmp;
-    for (uint32_t b = 0; b <= grid; ++b) cut[b] = base[b] = (int64_t)((uint64_t)units * b / grid);
+    constexpr int64_t Q = 4; // model resolution: quarter units
+    std::vector<int64_t> base(grid + 1), cut(grid + 1), start(grid), fin(grid), pre(grid + 1), suf(grid + 2);
+    for (uint32_t b = 0; b <= grid; ++b) base[b] = (int64_t)((uint64_t)units * b / grid);
+    double start_sum = 0;
+    for (uint32_t i = 0; i < grid; ++i) {
+        start[i] = (int64_t)(Q * late * late_profile((i + 0.5) / grid) + 0.5);
+        start_sum += (double)start[i];
+    }
+    {   // water filling: everybody finishes at `level`
+        const double level = ((double)Q * units + start_sum) / grid;
+        double acc = 0;
+        cut[0] = 0;
+        for (uint32_t i = 0; i < grid; ++i) {
+            acc += (level - (double)start[i]) / Q;
+            int64_t c = (int64_t)(acc + 0.5);
+            c = std::max(c, cut[i] + 1);                                  // >= 1 unit each
+            c = std::min(c, (int64_t)units - (int64_t)(grid - 1 - i));     // ... also for the rest
+            c = std::min(std::max(c, base[i + 1] - 100), base[i + 1] + 100);
+            cut[i + 1] = c;
+        }
+        cut[grid] = units;
+    }
+    const int64_t lat_q = Q * lat;
     // modelled finish time of CTA i
     auto fin_of = [&](uint32_t i) {
         const int64_t len = cut[i + 1] - cut[i];
-        int64_t f = len;
-        if (len > 0) {
+        int64_t f = start[i] + Q * len;
+        if (len > 0 && lat > 0) {
             const int64_t head = (cut[i + 1] - 1) / k_tiles * k_tiles, tile_end = head + k_tiles;
             if (head >= cut[i] && tile_end > cut[i + 1]) // reducer of a tile that goes on
                 for (uint32_t j = i + 1; j < grid && cut[j] < tile_end; ++j) {
                     const int64_t seg_end = (cut[j + 1] < tile_end ? cut[j + 1] : tile_end) - cut[j];
-                    if (seg_end + lat > f) f = seg_end + lat;
+                    f = std::max(f, start[j] + Q * seg_end + lat_q);
                 }
         }
         return f;
@@ -1570,9 +1607,16 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream,
             const char *e = std::getenv("PETIT_TILT_UNITS");
             return e ? std::atoi(e) : -1;
         }();
+        static const int late_env = [] {
+            const char *e = std::getenv("PETIT_TILT_LATE");
+            return e ? std::atoi(e) : -1;
+        }();
         const int lat = lat_env >= 0 ? lat_env : (NTOK <= 32 ? 5 : 3);
-        if (lat > 0)
-            tilt_cuts((uint32_t)units, (uint32_t)(args.k / kTileK), grid, lat, largs.cut_adj);
+        // the head start is worth ~4.5 units of a 16-token tile; only launches chained by
+        // programmatic dependent launch see it
+        const int late = !args.use_pdl ? 0 : (late_env >= 0 ? late_env : (NTOK <= 32 ? 4 : 3));
+        if (lat > 0 || late > 0)
+            tilt_cuts((uint32_t)units, (uint32_t)(args.k / kTileK), grid, lat, late, largs.cut_adj);
     }
     cudaError_t e;
     if constexpr (GR)

@@ -104,6 +104,28 @@ constexpr int kSetupBarId = 2;
 constexpr int kTeamBarId0 = 3; // 3, 4, 5: one named barrier per epilogue team
 constexpr int kSmemBudget = 227 * 1024;
 
+// Accumulator organisation of the 32- and 64-token tiles (experiment switches, see Cfg).
+// Measured (profiles/r02_mid_m_ab.md): more chains do not help either tile (the MMAs are not
+// latency-bound there); a second accumulator buffer for the 64-token tile (2 x 2 chains x 64
+// columns, leaving two TMEM A stages) lets the epilogue overlap the next tile: gate_up M=64
+// 71.2 -> 68.8 us, M=128 (two 64-token tiles) 141 -> 135 us, qkv M=128 30.5 -> 29.0 us;
+// 128-k stages for the 64-token tile are 15 % slower.
+#ifndef PETIT_NUMACC_32
+#define PETIT_NUMACC_32 2
+#endif
+#ifndef PETIT_NUMACC_64
+#define PETIT_NUMACC_64 2
+#endif
+#ifndef PETIT_ACC_COLS_32
+#define PETIT_ACC_COLS_32 128
+#endif
+#ifndef PETIT_ACC_COLS_64
+#define PETIT_ACC_COLS_64 256
+#endif
+#ifndef PETIT_KS_64
+#define PETIT_KS_64 256   // k extent of a stage of the 64-token tile
+#endif
+
 template <int MODE, int NTOK, int KS> struct Cfg {
     static constexpr bool kIsMx = MODE == kModeMxBf16;
     static constexpr bool kIsBf16 = MODE == kModeNvBf16 || MODE == kModeMxBf16;
@@ -145,8 +167,12 @@ template <int MODE, int NTOK, int KS> struct Cfg {
     // (Measured: 8 chains with a single accumulator buffer is slower than 4 chains
     // double-buffered -- the segment-boundary stall costs more than the extra chains
     // gain.)
-    static constexpr int kNumAcc = (NTOK <= 32 || NTOK == 128) ? 2 : 1;
-    static constexpr int kChains = NTOK >= 128 ? 1 : 128 / (kNumAcc * NTOK);
+    static constexpr int kNumAcc = NTOK == 32   ? PETIT_NUMACC_32
+                                   : NTOK == 64 ? PETIT_NUMACC_64
+                                                : ((NTOK <= 32 || NTOK == 128) ? 2 : 1);
+    // TMEM columns of all accumulators of a decode tile (the rest holds the A stages)
+    static constexpr int kDecodeAccCols = NTOK == 32 ? PETIT_ACC_COLS_32 : (NTOK == 64 ? PETIT_ACC_COLS_64 : 128);
+    static constexpr int kChains = NTOK >= 128 ? 1 : kDecodeAccCols / (kNumAcc * NTOK);
     // When a stage has fewer chunks than k-slice warps (KS = 64), the warps form
     // kGroups groups that take alternate stages.
     // Prefill tiles (NTOK >= 128) are tensor-bound: only half of the dequant warps
@@ -1631,7 +1657,7 @@ template <int MODE> int launch_grouped_mode(const GemmArgs &args, int ntok, cons
     switch (ntok) {
     case 16: return launch_variant<MODE, 16, 256, false, false, true>(args, num_sms, stream, &table);
     case 32: return launch_variant<MODE, 32, 256, false, false, true>(args, num_sms, stream, &table);
-    case 64: return launch_variant<MODE, 64, 256, false, false, true>(args, num_sms, stream, &table);
+    case 64: return launch_variant<MODE, 64, PETIT_KS_64, false, false, true>(args, num_sms, stream, &table);
     default: return kLaunchNoKernel;
     }
 }
@@ -1646,14 +1672,14 @@ template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
         switch (ntok) {
         case 16: return launch_variant<MODE, 16, 256, false, true>(args, num_sms, stream);
         case 32: return launch_variant<MODE, 32, 256, false, true>(args, num_sms, stream);
-        case 64: return launch_variant<MODE, 64, 256, false, true>(args, num_sms, stream);
+        case 64: return launch_variant<MODE, 64, PETIT_KS_64, false, true>(args, num_sms, stream);
         default: return kLaunchNoKernel;
         }
     }
     switch (ntok) {
     case 16: return launch_variant<MODE, 16, 256>(args, num_sms, stream);
     case 32: return launch_variant<MODE, 32, 256>(args, num_sms, stream);
-    case 64: return launch_variant<MODE, 64, 256>(args, num_sms, stream);
+    case 64: return launch_variant<MODE, 64, PETIT_KS_64>(args, num_sms, stream);
     case 128:
         return cluster_ok ? launch_variant<MODE, 128, 128, true>(args, num_sms, stream)
                           : launch_variant<MODE, 128, 128>(args, num_sms, stream);

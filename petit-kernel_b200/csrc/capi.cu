@@ -502,6 +502,18 @@ int petit_gemm_mxfp4_a16_ex(void *c, const void *a, const void *b, const void *s
                      reinterpret_cast<cudaStream_t>(stream), ar, epilogue);
 }
 
+/* Test hook (not in petit.h): the stream-K range cuts for `units` units in tiles of `k_tiles`
+ * on `grid` CTAs; cuts[b] = first unit of CTA b, cuts[grid] = units.  Returns 0, -1 on bad input. */
+int petit_debug_stream_k_cuts(unsigned units, unsigned k_tiles, unsigned grid, int lat, int late,
+                              unsigned *cuts) {
+    if (!cuts || grid == 0 || grid > gemm::kMaxGrid || k_tiles == 0 || units < grid) return -1;
+    int8_t adj[gemm::kMaxGrid + 4];
+    gemm::debug_stream_k_cuts(units, k_tiles, grid, lat, late, adj);
+    for (unsigned b = 0; b <= grid; ++b)
+        cuts[b] = (unsigned)((long long)((unsigned long long)units * b / grid) + adj[b]);
+    return 0;
+}
+
 int petit_gemm_fp4_a16_grouped(const PetitGroupedProblem *problems, unsigned num_groups, unsigned n,
                                unsigned k, const PetitSolutionHints *hints, uint64_t solution_id,
                                const PetitEpilogue *epilogue, petit_stream_t stream) {

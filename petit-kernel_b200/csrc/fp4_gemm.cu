@@ -1692,6 +1692,12 @@ template <int MODE> int launch_mode(const GemmArgs &args, int ntok, int num_sms,
 
 } // namespace
 
+void debug_stream_k_cuts(uint32_t units, uint32_t k_tiles, uint32_t grid, int lat, int late,
+                          int8_t *adj) {
+    std::memset(adj, 0, kMaxGrid + 4);
+    if (lat > 0 || late > 0) tilt_cuts(units, k_tiles, grid, lat, late, adj); // as the launcher
+}
+
 size_t workspace_partials_bytes() {
     return (size_t)kMaxGrid * kTileN * 256 * sizeof(float);
 }

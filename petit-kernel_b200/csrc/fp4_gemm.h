@@ -76,6 +76,10 @@ struct GroupTable {
     GroupEntry e[kMaxGroupTiles];
 };
 
+// test hook: the range cuts the launcher would use; adj must hold kMaxGrid + 4 entries
+void debug_stream_k_cuts(uint32_t units, uint32_t k_tiles, uint32_t grid, int lat, int late,
+                         int8_t *adj);
+
 size_t workspace_partials_bytes();
 size_t workspace_counters_bytes(); // kMaxTiles counters + the status word (last)
 

@@ -377,3 +377,60 @@ def test_cpp_source_compat_header_compiles_and_host_calls_work(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "compat host checks ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
 
+
+
+def test_stream_k_cuts_are_a_partition(lib):
+    """The launcher's range cuts (role / arrival model, csrc/fp4_gemm.cu tilt_cuts) must stay a
+    partition of the unit space whatever the model decides: strictly increasing, every CTA at
+    least one unit, within a signed byte of the equal split, and deterministic."""
+    import random
+
+    rng = random.Random(3)
+    shapes = [(80 * 32, 32, 148), (64 * 32, 32, 148), (64 * 112, 112, 148), (448 * 32, 32, 148),
+              (64 * 14, 14, 148), (592, 112, 148), (2560, 32, 132), (4 * 160, 7, 160)]
+    for _ in range(12):
+        k_tiles = rng.choice([1, 2, 3, 8, 14, 32, 56, 112])
+        grid = rng.choice([16, 64, 132, 148, 160])
+        tiles = rng.randint(max(1, 4 * grid // k_tiles + 1), 600)
+        shapes.append((tiles * k_tiles, k_tiles, grid))
+    for units, k_tiles, grid in shapes:
+        if units < 4 * grid:
+            continue
+        for lat, late in ((5, 4), (3, 0), (0, 4), (7, 8)):
+            cuts = (ctypes.c_uint * (grid + 1))()
+            assert lib.petit_debug_stream_k_cuts(units, k_tiles, grid, lat, late, cuts) == 0
+            c = list(cuts)
+            assert c[0] == 0 and c[grid] == units, (units, k_tiles, grid, lat, late)
+            assert all(b > a for a, b in zip(c, c[1:])), (units, k_tiles, grid, lat, late)
+            assert all(abs(c[b] - units * b // grid) <= 127 for b in range(grid + 1))
+            again = (ctypes.c_uint * (grid + 1))()
+            lib.petit_debug_stream_k_cuts(units, k_tiles, grid, lat, late, again)
+            assert list(again) == c
+        # the model must not make its own objective worse than the equal split
+        eq = (ctypes.c_uint * (grid + 1))()
+        lib.petit_debug_stream_k_cuts(units, k_tiles, grid, 0, 0, eq)
+        assert list(eq) == [units * b // grid for b in range(grid + 1)]
+    assert lib.petit_debug_stream_k_cuts(10, 32, 148, 5, 4, (ctypes.c_uint * 149)()) == -1
+    assert lib.petit_debug_stream_k_cuts(1000, 32, 148, 5, 4, None) == -1
+
+
+def test_grouped_gemm_host_side_checks(lib):
+    """petit_gemm_fp4_a16_grouped: argument errors are reported before any device work; an
+    all-empty group list is a no-op that succeeds without a device."""
+
+    class Prob(ctypes.Structure):
+        _fields_ = [("c", ctypes.c_void_p), ("a", ctypes.c_void_p), ("b", ctypes.c_void_p),
+                    ("scales", ctypes.c_void_p), ("gs", ctypes.c_void_p), ("m", ctypes.c_uint)]
+
+    class Epi(ctypes.Structure):
+        _fields_ = [("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
+                    ("activation", ctypes.c_int32), ("weight_layout", ctypes.c_int32)]
+
+    h = Hints(BF16, FP4, BF16, 0)
+    probs = (Prob * 3)()  # three groups with m = 0
+    auto = ctypes.c_uint64(2 ** 64 - 1)
+    assert lib.petit_gemm_fp4_a16_grouped(probs, 3, 1024, 2048, ctypes.byref(h), auto, None, None) == 0
+    assert lib.petit_gemm_fp4_a16_grouped(None, 3, 1024, 2048, ctypes.byref(h), auto, None, None) == 1
+    assert lib.petit_gemm_fp4_a16_grouped(probs, 3, 1024, 2048, None, auto, None, None) == 2
+    epi = Epi(None, 0x1000, 0, 0)  # a residual cannot be shared by groups of different sizes
+    assert lib.petit_gemm_fp4_a16_grouped(probs, 3, 1024, 2048, ctypes.byref(h), auto, ctypes.byref(epi), None) == 1

@@ -486,23 +486,42 @@ def main():
             else:
                 pk.mul_nvfp4_a16(acts[k], b, sp, gs, m, n, k, -1)
 
-        for i in range(3):
-            one(i)
-        sync()
-        reps = 20
-        e0.record()
-        for i in range(reps):
-            one(i)
-        e1.record()
-        torch.cuda.synchronize()
-        tl = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device=dev)
-        if world > 1:
-            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
-        us = tl.item()
-        per_launch.append({"gemm": nm, "n": n, "k": k, "us": round(us, 2),
-                           "gbs": round(algo_bytes(m, n, k) / us * 1e-3, 1),
-                           "frac_hbm": round(algo_bytes(m, n, k) / us * 1e-3 / hbm_peak, 4),
-                           "includes_allreduce": bool(with_ar)})
+        def timed_us(fn, reps=20):
+            for i in range(3):
+                fn(i)
+            sync()
+            e0.record()
+            for i in range(reps):
+                fn(i)
+            e1.record()
+            torch.cuda.synchronize()
+            tl = torch.tensor([e0.elapsed_time(e1) / reps * 1e3], device=dev)
+            if world > 1:
+                dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            return tl.item()
+
+        us = timed_us(one)
+        row = {"gemm": nm, "n": n, "k": k, "us": round(us, 2),
+               "gbs": round(algo_bytes(m, n, k) / us * 1e-3, 1),
+               "frac_hbm": round(algo_bytes(m, n, k) / us * 1e-3 / hbm_peak, 4),
+               "includes_allreduce": bool(with_ar)}
+        if with_ar:
+            # the same shard GEMM without the exchange: what the fused all-reduce adds
+            def plain(i):
+                b, sp = layers[i % copies][names0.index(nm)][4:6]
+                pk.mul_nvfp4_a16(acts[k], b, sp, gs, m, n, k, -1)
+
+            row["gemm_only_us"] = round(timed_us(plain), 2)
+        per_launch.append(row)
+    tp_breakdown = None
+    if world > 1:
+        col = sum(p["us"] for p in per_launch if not p["includes_allreduce"])
+        row_fused = sum(p["us"] for p in per_launch if p["includes_allreduce"])
+        row_plain = sum(p.get("gemm_only_us", 0.0) for p in per_launch if p["includes_allreduce"])
+        tp_breakdown = {"column_parallel_gemm_us": round(col, 2), "row_parallel_gemm_only_us": round(row_plain, 2),
+                        "row_parallel_with_allreduce_us": round(row_fused, 2),
+                        "allreduce_extra_us": round(row_fused - row_plain, 2) if row_plain else None,
+                        "note": "per-launch event times, max over ranks; the step overlaps neighbours by PDL"}
     shard_bytes = sum(algo_bytes(m, n, k) for _, n, k, _ in shard)
     avg_launch_us = sum(p["us"] for p in per_launch) / len(per_launch)
     achieved = (shard_bytes / len(shard)) / avg_launch_us * 1e-3
@@ -596,6 +615,8 @@ def main():
         out["tp_check"] = tp_check
     if tp_m_sweep is not None:
         out["tp_m_sweep"] = tp_m_sweep
+    if tp_breakdown is not None:
+        out["tp_breakdown"] = tp_breakdown
     if details:
         out["details"] = details
     print(json.dumps(out))

@@ -1,8 +1,8 @@
 #!/bin/bash
 # Build an experiment copy of libpetit_b200.so:
 #   tools/build_variant.sh <name> [<src root>] [--patch FILE]... [nvcc flags...]
-# e.g. tools/build_variant.sh g2 . -DPETIT_DECODE_GROUPS_NVBF16=2
-#      tools/build_variant.sh swpipe . --patch tools/variant_patches/swpipe_sttm.patch
+# e.g. tools/build_variant.sh c64 . -DPETIT_ACC_COLS_64=128 -DPETIT_NUMACC_64=1
+#      tools/build_variant.sh mine . --patch my_experiment.patch
 # A --patch is applied (patch -p0 from the source root) to a scratch copy of csrc/, never to
 # the tree.  The copy of the library lands in variants/<name>/ (git-ignored, travels with
 # gpurun); run any tool against it with LD_LIBRARY_PATH=variants/<name> (the tools and the

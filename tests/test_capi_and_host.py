@@ -434,3 +434,28 @@ def test_grouped_gemm_host_side_checks(lib):
     assert lib.petit_gemm_fp4_a16_grouped(probs, 3, 1024, 2048, None, auto, None, None) == 2
     epi = Epi(None, 0x1000, 0, 0)  # a residual cannot be shared by groups of different sizes
     assert lib.petit_gemm_fp4_a16_grouped(probs, 3, 1024, 2048, ctypes.byref(h), auto, ctypes.byref(epi), None) == 1
+
+
+def test_shipped_tune_table_loads_and_mostly_agrees_with_the_rule(lib):
+    """petit_kernel/tuned/llama3_70b_b200.tune (tools/make_tune_table.py from the committed sweep
+    log): every line is accepted by the loader, and the built-in rule already picks the measured
+    winner for most of the listed problems (the table exists for the ones where it does not)."""
+    path = os.path.join(ROOT, "petit-kernel_b200", "petit_kernel", "tuned", "llama3_70b_b200.tune")
+    rows = [l.split("#")[0].split() for l in open(path) if l.split("#")[0].strip()]
+    assert len(rows) >= 40
+    lib.petit_tune_table_clear()
+    h = Hints(BF16, FP4, BF16, 0)
+    agree = 0
+    for bt, at, m, n, k, hexid in rows:
+        sid = ctypes.c_uint64(0)
+        assert lib.petit_get_default_solution(ctypes.byref(h), int(m), int(n), int(k), ctypes.byref(sid)) == 0
+        agree += sid.value == int.from_bytes(bytes.fromhex(hexid), "little")
+    assert agree >= 0.75 * len(rows), (agree, len(rows))
+    try:
+        assert lib.petit_tune_table_load(path.encode()) == len(rows)
+        for bt, at, m, n, k, hexid in rows:
+            sid = ctypes.c_uint64(0)
+            lib.petit_get_default_solution(ctypes.byref(h), int(m), int(n), int(k), ctypes.byref(sid))
+            assert sid.value == int.from_bytes(bytes.fromhex(hexid), "little")
+    finally:
+        lib.petit_tune_table_clear()

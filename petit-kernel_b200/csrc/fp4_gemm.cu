@@ -1593,6 +1593,7 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream,
     const uint64_t m_tiles = GR ? table->tiles : (args.m + NTOK - 1) / NTOK;
     const uint64_t units = (CL ? n_tiles / 2 : n_tiles) * m_tiles * (args.k / kTileK);
     unsigned grid = (unsigned)(units < (uint64_t)num_sms ? units : (uint64_t)num_sms);
+    bool whole_tiles = false; // one whole tile per CTA: the cuts must stay on tile boundaries
     // Small shards (TP-8 o_proj: 64 tiles x 4 k-tiles on 148 SMs): with < ~2 units per SM every
     // tile would be cut between CTAs that all finish together, and the split-tile hand-shake
     // (~2 us) would be most of the launch.  One whole tile per CTA on fewer SMs is faster there
@@ -1603,8 +1604,10 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream,
             return e ? std::atoi(e) : 1;
         }();
         const uint64_t tiles = n_tiles * m_tiles, k_tiles = args.k / kTileK;
-        if (whole && tiles <= (uint64_t)num_sms && tiles * 3 >= (uint64_t)num_sms && k_tiles <= 6)
+        if (whole && tiles <= (uint64_t)num_sms && tiles * 3 >= (uint64_t)num_sms && k_tiles <= 6) {
             grid = (unsigned)tiles;
+            whole_tiles = true;
+        }
     }
     if (CL) {
         const uint64_t clusters = units < (uint64_t)(num_sms / 2) ? units : (uint64_t)(num_sms / 2);
@@ -1628,7 +1631,10 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream,
     cfg.numAttrs = CL ? 2 : 1;
     GemmArgs largs = args;
     std::memset(largs.cut_adj, 0, sizeof(largs.cut_adj));
-    if (!CL && NTOK <= 64 && grid > 1 && units >= 4ull * grid) {
+    // Not for whole-tile grids, and not for small shards (< 8 units per CTA): there the model's
+    // few units of latency are most of a range, and the TP-8 step got slower with it (o_proj +
+    // all-reduce 24 -> 38 us when its whole-tile grid was cut up again).
+    if (!CL && NTOK <= 64 && grid > 1 && !whole_tiles && units >= 8ull * grid) {
         static const int lat_env = [] {
             const char *e = std::getenv("PETIT_TILT_UNITS");
             return e ? std::atoi(e) : -1;
@@ -1640,7 +1646,8 @@ int launch_variant(const GemmArgs &args, int num_sms, cudaStream_t stream,
         const int lat = lat_env >= 0 ? lat_env : (NTOK <= 32 ? 5 : 3);
         // the head start is worth ~4.5 units of a 16-token tile; only launches chained by
         // programmatic dependent launch see it
-        const int late = !args.use_pdl ? 0 : (late_env >= 0 ? late_env : (NTOK <= 32 ? 4 : 3));
+        // (the arrival term is only measured for plain GEMMs: none under the fused all-reduce)
+        const int late = (!args.use_pdl || AR) ? 0 : (late_env >= 0 ? late_env : (NTOK <= 32 ? 4 : 3));
         if (lat > 0 || late > 0)
             tilt_cuts((uint32_t)units, (uint32_t)(args.k / kTileK), grid, lat, late, largs.cut_adj);
     }
